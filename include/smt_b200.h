@@ -1,0 +1,165 @@
+/*
+ * smt_b200.h — C-ABI of the B200-native SMT (Sparse Matrix Tuning) hot path.
+ *
+ * The reference (yudaohai666/Sparse_Matrix_Tuning) has no native interface: its
+ * hot path is eager PyTorch inside `deepspeed/smt/smt.py`, `deepspeed/smt/smt_helper.py`
+ * and three snippets of `deepspeed/fine_tune.py`.  Each entry point below replaces one
+ * of those Python call sites (cited per function, paths relative to the reference root)
+ * and is what a maintainer would bind with ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`;
+ *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream);
+ *   - return value: 0 = ok, negative = error; `smt_last_error()` returns a thread-local
+ *     message for the calling thread (forward runs on the caller thread, backward on the
+ *     autograd worker thread, so nothing here keeps cross-thread mutable state);
+ *   - no allocation inside: workspaces are sized by the `*_workspace_bytes` twins;
+ *   - matrices are row-major, `ld*` are leading dimensions in ELEMENTS;
+ *   - a weight matrix is `W[out_features, in_features]`; block (r, c) covers
+ *     `W[r*b:(r+1)*b, c*b:(c+1)*b]` (reference smt.py:319-325), b in {64, 128, 256};
+ *   - "compact" storage stacks block i at rows [i*b, (i+1)*b) of an `[n*b, b]` matrix,
+ *     i.e. at flat element offset i*b*b (reference smt.py:312-325).
+ */
+#ifndef SMT_B200_H_
+#define SMT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define SMT_API __attribute__((visibility("default")))
+#else
+#define SMT_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* element types */
+enum { SMT_F32 = 0, SMT_BF16 = 1, SMT_F16 = 2 };
+
+/* block-score strategies (reference smt_helper.py:233-251) */
+enum { SMT_MEAN_ABS = 0,  /* |mean(g)|   smt_helper.py:233 */
+       SMT_ABS_MEAN = 1,  /* mean(|g|)   smt_helper.py:238 */
+       SMT_L1       = 2,  /* sum(|g|)    smt_helper.py:243 */
+       SMT_L2       = 3   /* sqrt(sum g^2) smt_helper.py:249 */ };
+
+/* error codes */
+enum { SMT_OK = 0, SMT_ERR_ARG = -1, SMT_ERR_CUDA = -2, SMT_ERR_UNSUPPORTED = -3,
+       SMT_ERR_WORKSPACE = -4 };
+
+/* One selected block of one weight matrix.  A table of these describes a whole model's
+ * selection: entry i owns compact flat offset i*b*b. */
+typedef struct smt_block_ref {
+  uint64_t w_ptr;   /* device address of the dense weight W this block lives in        */
+  int64_t  ldw;     /* leading dimension of W, elements                                */
+  int32_t  row;     /* block row    (out_features / b index)                           */
+  int32_t  col;     /* block column (in_features  / b index)                           */
+} smt_block_ref;
+
+SMT_API const char* smt_last_error(void);
+SMT_API int  smt_version(void);
+/* sm_count / compute capability of the current device. */
+SMT_API int  smt_device_info(int* sm_count_host, int* cc_major_host, int* cc_minor_host);
+
+/* ---- warm-up scoring ------------------------------------------------------------- */
+
+/* acc[i] += (float)grad[i]   — replaces the D2H copy + CPU `+=` of fine_tune.py:724-740,751-765. */
+SMT_API int smt_score_accumulate(float* acc, const void* grad, int grad_dtype, int64_t n, void* stream);
+
+/* block_sums[R/b, C/b] += sum over each b x b tile of grad[R, C] (signed sums).
+ * Linear in g, hence valid for SMT_MEAN_ABS only (= what q/k/v always use, fine_tune.py:306-313). */
+SMT_API int smt_block_sum_accumulate(float* block_sums, const void* grad, int grad_dtype,
+                             int rows, int cols, int64_t ld, int block, void* stream);
+
+/* scores[i] = |block_sums[i]| / b^2  (mean_abs from accumulated signed block sums). */
+SMT_API int smt_block_sum_finalize(const float* block_sums, float* scores, int64_t n, int block, void* stream);
+
+/* scores[R/b, C/b] = strategy over each b x b tile of acc[R, C] — smt_helper.py:55-78, 233-251. */
+SMT_API int smt_block_score_reduce(const float* acc, int rows, int cols, int64_t ld, int block,
+                           int strategy, float* scores, void* stream);
+
+/* acc[S, C] += sum_b |x[b, S, C]|  — the activation hook of fine_tune.py:649-678 reduced over the
+ * batch dimension, which is all smt_helper.py:170 consumes. */
+SMT_API int smt_act_score_accumulate(float* acc, const void* x, int x_dtype, int batch, int seq, int channels,
+                             void* stream);
+
+/* out[C] = strategy over the S rows of acc[S, C]  — smt_helper.py:172-183 (acc is already >= 0). */
+SMT_API int smt_channel_score_reduce(const float* acc, int seq, int channels, int strategy, float* out,
+                             void* stream);
+
+/* ---- top-k selection ---------------------------------------------------------------- */
+
+/* Segmented top-k over `scores[N]`.  Segment s covers [seg_offsets[s], seg_offsets[s+1]) and keeps
+ * its k_s = min(seg_k[s], length) best entries, written best-first as flat indices into [0, N) at
+ * out_idx[out_offsets[s] ...].  Order: descending score; equal scores are ordered by descending
+ * `tiebreak_rank` (unique within a segment; NULL = the flat index).  This is Python's tuple order on
+ * (score, ((module, layer), i, j)) used by the heap in smt_helper.py:111-130 once the host has
+ * ranked the tuples.  `inv_rank[rank] = flat index` (NULL when tiebreak_rank is NULL).
+ * One segment = `no_restriction` (smt_helper.py:102-146); one segment per matrix = `norm_dist`
+ * (smt_helper.py:81-100).  NaN scores are not supported (the reference's order is unspecified). */
+SMT_API size_t smt_topk_workspace_bytes(int64_t n_scores);
+SMT_API int smt_topk_blocks(const float* scores, const uint32_t* tiebreak_rank, const uint32_t* inv_rank,
+                    int64_t n_scores, const int32_t* seg_offsets, const int32_t* seg_k,
+                    const int32_t* out_offsets, int num_segments, int32_t* out_idx,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- compact <-> dense block movement ------------------------------------------------ */
+
+/* compact[i] <- W_i[block]  — LinearLayer_MatrixSparsity.__init__, smt.py:317-325. */
+SMT_API int smt_block_gather(const smt_block_ref* table, int n_blocks, int block, int elem_bytes,
+                     void* compact, void* stream);
+/* W_i[block] <- compact[i]  — the scatter loop of forward, smt.py:332-341, and
+ * convert_matrix_sparsity_to_linear_layer, smt.py:427-439. */
+SMT_API int smt_block_scatter(const smt_block_ref* table, int n_blocks, int block, int elem_bytes,
+                      const void* compact, void* stream);
+
+/* ---- block-gradient contraction (linearZ.backward, smt.py:386-404) -------------------- */
+
+/* G[i*b + o, k] (+)= sum_t dy[t, row_i*b + o] * x[t, col_i*b + k],  t in [0, T).
+ * x: [T, in_features] (ldx), dy: [T, out_features] (lddy), both `in_dtype`.
+ * bf16/f16 inputs run the TMA-fed tcgen05/TMEM grouped kernel with fp32 accumulation over all T
+ * (one rounding, to `out_dtype`); f32 inputs run an fp32 FMA kernel (exact-order-free, 1e-5 class).
+ * `block_rc` is a device int32 [n_blocks][2] table of (row, col).
+ * `accumulate` != 0 adds into G instead of overwriting it. */
+SMT_API size_t smt_block_grad_gemm_workspace_bytes(int n_blocks, int block, int64_t T, int in_dtype);
+SMT_API int smt_block_grad_gemm(const void* x, int64_t ldx, int in_features,
+                        const void* dy, int64_t lddy, int out_features,
+                        int64_t T, int in_dtype,
+                        const int32_t* block_rc, int n_blocks, int block,
+                        void* G, int out_dtype, int accumulate,
+                        void* workspace, size_t workspace_bytes, void* stream);
+/* introspection for tests/bench: split-K factor and CTA count the launch above would use. */
+SMT_API int smt_block_grad_gemm_plan(int n_blocks, int block, int64_t T, int in_dtype,
+                             int* splits_host, int* ctas_host);
+
+/* ---- compact optimizer ---------------------------------------------------------------- */
+
+/* out_sqnorm[0] = sum grad[i]^2 (fp32, deterministic two-stage tree). workspace: 4 KiB floats. */
+SMT_API size_t smt_grad_sqnorm_workspace_bytes(void);
+SMT_API int smt_grad_sqnorm(const void* grad, int grad_dtype, int64_t n, float* out_sqnorm,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* AdamW step (DeepSpeed FusedAdam adam_w_mode, fine_tune.py:352-363) over the flat compact state,
+ * fused with global-norm clipping (deepspeed_helpers.py:87) and with the write-back of the updated
+ * blocks into the dense weights (smt.py:332-341), so no scatter is needed in forward.
+ *   g      = grad * grad_scale * clip,   clip = min(1, max_norm / (grad_scale*sqrt(*sqnorm) + 1e-6))
+ *            (clip = 1 when sqnorm == NULL or max_norm <= 0)
+ *   m      = b1*m + (1-b1)*g ;  v = b2*v + (1-b2)*g*g
+ *   update = (m/bc1) / (sqrt(v/bc2) + eps) + wd*p ;  p -= lr*update        (p = fp32 master)
+ * then compact_out[i] (optional) and W blocks (optional, via `table`) receive p rounded to their
+ * dtype.  bias corrections bc1/bc2 are passed by the host (1 - beta^step, computed in double). */
+SMT_API int smt_compact_adam(float* master, float* exp_avg, float* exp_avg_sq,
+                     const void* grad, int grad_dtype, int64_t n_elems,
+                     float lr, float beta1, float beta2, float eps, float weight_decay,
+                     float bias_correction1, float bias_correction2,
+                     float grad_scale, const float* sqnorm, float max_norm,
+                     void* compact_out, int compact_dtype,
+                     const smt_block_ref* table, int n_blocks, int block, int w_dtype,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* SMT_B200_H_ */

@@ -1,0 +1,617 @@
+// Block-gradient contraction of linearZ.backward (reference deepspeed/smt/smt.py:386-404):
+//
+//     G[i*b + o, k] = sum_t dy[t, row_i*b + o] * x[t, col_i*b + k]          for every selected block i
+//
+// The reference issues, per block, a batched cuBLAS bmm ([B,b,S]x[B,S,b]), a reduction over the batch and
+// a slice copy (3 launches per block, results rounded to bf16 per batch entry).  Here ONE grouped launch
+// covers every block of the module: a TMA-fed tcgen05/TMEM GEMM with fp32 accumulation over all T tokens
+// and a single final rounding.
+//
+// Operand layout.  The reduction dimension is the token index t, the SLOW dimension of both row-major
+// inputs, so both UMMA operands are "MN-major": A[m,k] = dy[k, row*b+m] has m contiguous, B[k,n] =
+// x[k, col*b+n] has n contiguous.  A TMA box of {64 features, K_TILE tokens} with 128-byte swizzle lands
+// in shared memory exactly as the canonical MN-major SWIZZLE_128B UMMA layout
+// ((8,n),(8,k)):((1,LBO),(8,SBO)) [units of 16 B]: 8 token rows of 128 B form one 1024-B swizzle atom
+// (SBO = 1024 B between 8-token groups) and consecutive 64-feature chunks are LBO = K_TILE*128 B apart.
+//
+// Work decomposition.  Work item = (block, K-split).  One CTA (6 warps: TMA producer, MMA issuer/TMEM
+// owner, 4 epilogue warps) computes the full b x b block for its token range: for b = 256 two M=128
+// accumulators share one x strip (N = 256), using all 512 TMEM columns, which gives the 256x256 tile its
+// 256 flop/B shared-memory-fill intensity.  With few blocks per module (about 9 at 0.71 %) the token range
+// is split across CTAs; partial tiles go to an fp32 workspace and a second kernel sums them in a fixed
+// order (deterministic, no atomics).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace smt {
+namespace {
+
+constexpr int kKTile = 64;                    // tokens per pipeline stage
+constexpr int kChunkBytes = kKTile * 128;     // one {64 features x K_TILE tokens} TMA box of 16-bit data
+constexpr int kGemmThreads = 192;             // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-5 epilogue
+constexpr int kSmemBudget = 200 * 1024;       // pipeline stages (dynamic smem), leaves room for barriers
+constexpr int kMinKTilesPerSplit = 4;
+
+template <int B>
+struct Cfg {
+  static constexpr int MH = B == 256 ? 2 : 1;            // M=128 halves per block
+  static constexpr int A_LOAD = B / 64;                  // A chunks fetched per stage
+  static constexpr int A_SLOTS = A_LOAD < 2 ? 2 : A_LOAD;  // M=128 always spans two chunks
+  static constexpr int B_LOAD = B / 64;                  // N = B
+  static constexpr int STAGE_BYTES = (A_SLOTS + B_LOAD) * kChunkBytes;
+  static constexpr int STAGES_RAW = kSmemBudget / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int TX_BYTES = (A_LOAD + B_LOAD) * kChunkBytes;
+  static constexpr int TMEM_COLS = MH * B < 32 ? 32 : MH * B;  // 512 / 128 / 64 (powers of two)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + alignment slack
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must trap, never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) {
+      printf("smt_block_grad_gemm: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x,
+             blockIdx.y, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
+                                            int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (bf16/f16 inputs, fp32 accumulate)
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once every previously issued tcgen05.mma has completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+        "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
+        "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
+        "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor, MN-major, SWIZZLE_128B (see header comment for the layout).
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);          // start address      bits [0,14)
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;     // leading byte off.  bits [16,30)
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;     // stride byte off.   bits [32,46)
+  d |= (uint64_t)1 << 46;                                // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                                // layout type SWIZZLE_128B
+  return d;
+}
+// Instruction descriptor for kind::f16: fp32 accumulate, A and B both MN-major.
+__host__ __device__ constexpr uint32_t make_idesc(int fmt /*0 = f16, 1 = bf16*/, int M, int N) {
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | (1u << 15) | (1u << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---- the tcgen05 kernel ----------------------------------------------------------------------------
+
+struct GemmParams {
+  const int32_t* block_rc;  // [n_blocks][2] (row, col)
+  void* out;                // G (final) when splits == 1, else fp32 workspace
+  int splits;
+  int kt_total;             // number of K tiles = ceil(T / kKTile)
+  int kt_per_split;
+  int out_dtype;            // of G; the workspace is always fp32
+  int accumulate;
+  int in_fmt;               // 0 = f16, 1 = bf16
+};
+
+template <int B, int ODT, bool ACC>
+__device__ __forceinline__ void store_row_chunk(void* out_base, int64_t elem_off, const uint32_t (&r)[32]) {
+  // 32 consecutive output elements of one row
+  if (ODT == SMT_F32) {
+    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(out_base) + elem_off);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                             __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+      if (ACC) {
+        const float4 old = o[q];
+        v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
+      }
+      o[q] = v;
+    }
+  } else {
+    uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(out_base) + elem_off);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[8 * q + j]);
+      if (ACC) {
+        float old[8];
+        unpack8<ODT>(o[q], old);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] += old[j];
+      }
+      uint4 u;
+      if (ODT == SMT_BF16) {
+        u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
+        u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+      } else {
+        u.x = pack_f16x2(f[0], f[1]); u.y = pack_f16x2(f[2], f[3]);
+        u.z = pack_f16x2(f[4], f[5]); u.w = pack_f16x2(f[6], f[7]);
+      }
+      o[q] = u;
+    }
+  }
+}
+
+template <int B>
+__global__ void __launch_bounds__(kGemmThreads, 1) block_grad_umma_kernel(
+    const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
+    const GemmParams p) {
+  using C = Cfg<B>;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[C::STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[C::STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int blk = blockIdx.x, split = blockIdx.y;
+  const int kt_begin = split * p.kt_per_split;
+  const int kt_end = min(kt_begin + p.kt_per_split, p.kt_total);
+  const int n_kt = kt_end - kt_begin;  // >= 1 by construction of the plan
+
+  // 1024-byte aligned pipeline buffers (SWIZZLE_128B atoms are 1024 B)
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  auto a_addr = [&](int stage) { return smem_base + stage * C::STAGE_BYTES; };
+  auto b_addr = [&](int stage) { return smem_base + stage * C::STAGE_BYTES + C::A_SLOTS * kChunkBytes; };
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_x);
+    prefetch_tmap(&tmap_dy);
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(&tmem_full_bar), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      const int row = p.block_rc[2 * blk], col = p.block_rc[2 * blk + 1];
+      for (int it = 0; it < n_kt; ++it) {
+        const int stage = it % C::STAGES;
+        const uint32_t phase = (uint32_t)(it / C::STAGES) & 1u;
+        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+        const uint32_t fb = smem_u32(&full_bar[stage]);
+        mbar_expect_tx(fb, C::TX_BYTES);
+        const int t0 = (kt_begin + it) * kKTile;
+#pragma unroll
+        for (int c = 0; c < C::A_LOAD; ++c)
+          tma_load_2d(a_addr(stage) + c * kChunkBytes, &tmap_dy, fb, row * B + c * 64, t0);
+#pragma unroll
+        for (int c = 0; c < C::B_LOAD; ++c)
+          tma_load_2d(b_addr(stage) + c * kChunkBytes, &tmap_x, fb, col * B + c * 64, t0);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(p.in_fmt, 128, B);
+      for (int it = 0; it < n_kt; ++it) {
+        const int stage = it % C::STAGES;
+        const uint32_t phase = (uint32_t)(it / C::STAGES) & 1u;
+        mbar_wait(smem_u32(&full_bar[stage]), phase);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < kKTile / 16; ++k) {
+          // 16 tokens = two 8-row swizzle atoms = 2048 B further down every chunk
+          const uint64_t bdesc = make_desc_mn_sw128(b_addr(stage) + k * 2048, kChunkBytes, 1024);
+#pragma unroll
+          for (int mh = 0; mh < C::MH; ++mh) {
+            const uint64_t adesc =
+                make_desc_mn_sw128(a_addr(stage) + mh * 2 * kChunkBytes + k * 2048, kChunkBytes, 1024);
+            umma_f16(tmem_base + mh * B, adesc, bdesc, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(smem_u32(&empty_bar[stage]));  // frees the smem stage when these MMAs retire
+      }
+      umma_commit(smem_u32(&tmem_full_bar));       // accumulators complete
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> global =====
+    const int q = warp & 3;             // TMEM lane quarter this warp may access
+    const int m = q * 32 + lane;        // accumulator row (0..127)
+    mbar_wait(smem_u32(&tmem_full_bar), 0);
+    tc_fence_after();
+    const bool final_out = (p.splits == 1);
+    const int64_t tile_elems = (int64_t)B * B;
+    constexpr int ROWS_VALID = B < 128 ? B : 128;
+#pragma unroll 1
+    for (int mh = 0; mh < C::MH; ++mh) {
+#pragma unroll 1
+      for (int cc = 0; cc < B / 32; ++cc) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mh * B + cc * 32), r);
+        tmem_ld_wait();
+        if (m < ROWS_VALID) {
+          const int64_t off_in_tile = (int64_t)(mh * 128 + m) * B + cc * 32;
+          if (!final_out) {
+            store_row_chunk<B, SMT_F32, false>(p.out, ((int64_t)blk * p.splits + split) * tile_elems + off_in_tile, r);
+          } else {
+            const int64_t off = (int64_t)blk * tile_elems + off_in_tile;
+            if (p.out_dtype == SMT_F32) {
+              if (p.accumulate) store_row_chunk<B, SMT_F32, true>(p.out, off, r);
+              else store_row_chunk<B, SMT_F32, false>(p.out, off, r);
+            } else if (p.out_dtype == SMT_BF16) {
+              if (p.accumulate) store_row_chunk<B, SMT_BF16, true>(p.out, off, r);
+              else store_row_chunk<B, SMT_BF16, false>(p.out, off, r);
+            } else {
+              if (p.accumulate) store_row_chunk<B, SMT_F16, true>(p.out, off, r);
+              else store_row_chunk<B, SMT_F16, false>(p.out, off, r);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ---- split-K reduction: G = sum_s partial[s] (fixed order) -----------------------------------------
+
+template <int ODT>
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, void* __restrict__ out,
+                                                            int64_t tile_elems, int splits, int64_t n_vec8,
+                                                            int accumulate) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t vec = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; vec < n_vec8; vec += stride) {
+    const int64_t e = vec * 8;
+    const int64_t blk = e / tile_elems, within = e - blk * tile_elems;
+    const float* src = ws + blk * splits * tile_elems + within;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int s = 0; s < splits; ++s) {
+      const float4 a = ld_stream_f4(src + (int64_t)s * tile_elems);
+      const float4 b = ld_stream_f4(src + (int64_t)s * tile_elems + 4);
+      acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+      acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+    }
+    if (ODT == SMT_F32) {
+      float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + e);
+      float4 v0 = make_float4(acc[0], acc[1], acc[2], acc[3]), v1 = make_float4(acc[4], acc[5], acc[6], acc[7]);
+      if (accumulate) {
+        const float4 o0 = o[0], o1 = o[1];
+        v0.x += o0.x; v0.y += o0.y; v0.z += o0.z; v0.w += o0.w;
+        v1.x += o1.x; v1.y += o1.y; v1.z += o1.z; v1.w += o1.w;
+      }
+      o[0] = v0;
+      o[1] = v1;
+    } else {
+      uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(out) + e);
+      if (accumulate) {
+        float old[8];
+        unpack8<ODT>(*o, old);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += old[j];
+      }
+      uint4 u;
+      if (ODT == SMT_BF16) {
+        u.x = pack_bf16x2(acc[0], acc[1]); u.y = pack_bf16x2(acc[2], acc[3]);
+        u.z = pack_bf16x2(acc[4], acc[5]); u.w = pack_bf16x2(acc[6], acc[7]);
+      } else {
+        u.x = pack_f16x2(acc[0], acc[1]); u.y = pack_f16x2(acc[2], acc[3]);
+        u.z = pack_f16x2(acc[4], acc[5]); u.w = pack_f16x2(acc[6], acc[7]);
+      }
+      *o = u;
+    }
+  }
+}
+
+// ---- fp32 path (parity configuration: fp32 models) --------------------------------------------------
+// 64x64 output tile per CTA, 16-token slabs staged in shared memory, 4x4 register micro-tile per thread.
+
+template <int ODT>
+__global__ void __launch_bounds__(256) block_grad_f32_kernel(const float* __restrict__ x, int64_t ldx,
+                                                             const float* __restrict__ dy, int64_t lddy,
+                                                             int64_t T, const int32_t* __restrict__ block_rc,
+                                                             int block, void* __restrict__ out, int accumulate) {
+  __shared__ float sa[16][64 + 4];  // dy slab  [t][m]
+  __shared__ float sb[16][64 + 4];  // x slab   [t][n]
+  const int blk = blockIdx.x;
+  const int tiles = block / 64;
+  const int tm = blockIdx.y / tiles, tn = blockIdx.y % tiles;
+  const int row = block_rc[2 * blk], col = block_rc[2 * blk + 1];
+  const float* a0 = dy + (int64_t)row * block + tm * 64;
+  const float* b0 = x + (int64_t)col * block + tn * 64;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16 threads, 4 x 4 each
+  const int lt = threadIdx.x >> 4, lc = (threadIdx.x & 15) * 4;  // loader: token lt, features lc..lc+3
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int64_t t0 = 0; t0 < T; t0 += 16) {
+    float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+    if (t0 + lt < T) {
+      va = *reinterpret_cast<const float4*>(a0 + (t0 + lt) * lddy + lc);
+      vb = *reinterpret_cast<const float4*>(b0 + (t0 + lt) * ldx + lc);
+    }
+    __syncthreads();
+    *reinterpret_cast<float4*>(&sa[lt][lc]) = va;
+    *reinterpret_cast<float4*>(&sb[lt][lc]) = vb;
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+      const float4 a = *reinterpret_cast<const float4*>(&sa[t][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&sb[t][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t off = ((int64_t)blk * block + tm * 64 + ty * 4 + i) * block + tn * 64 + tx * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float v = acc[i][j];
+      if (accumulate) v += load_as_float<ODT>(out, off + j);
+      store_from_float<ODT>(out, off + j, v);
+    }
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------
+
+struct Plan {
+  int splits, kt_total, kt_per_split;
+};
+
+Plan make_plan(int n_blocks, int64_t T) {
+  Plan pl;
+  pl.kt_total = (int)((T + kKTile - 1) / kKTile);
+  int splits = sm_count() / (n_blocks > 0 ? n_blocks : 1);
+  int max_by_work = pl.kt_total / kMinKTilesPerSplit;
+  if (splits > max_by_work) splits = max_by_work;
+  if (splits < 1) splits = 1;
+  pl.kt_per_split = (pl.kt_total + splits - 1) / splits;
+  pl.splits = (pl.kt_total + pl.kt_per_split - 1) / pl.kt_per_split;  // drop empty tails
+  return pl;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+// 2-D map over a row-major [T, features] 16-bit matrix; box = {64 features, kKTile tokens}, 128B swizzle.
+int encode_operand_map(CUtensorMap* map, const void* base, int64_t features, int64_t T, int64_t ld, int in_dtype) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    set_error("smt_block_grad_gemm: cuTensorMapEncodeTiled not available from the driver");
+    return SMT_ERR_CUDA;
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)features, (cuuint64_t)T};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {64, (cuuint32_t)kKTile};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, in_dtype == SMT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                   const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("smt_block_grad_gemm: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return SMT_ERR_CUDA;
+  }
+  return SMT_OK;
+}
+
+template <int B>
+int launch_umma(const CUtensorMap& mx, const CUtensorMap& mdy, const GemmParams& gp, int n_blocks, cudaStream_t st) {
+  using C = Cfg<B>;
+  SMT_CHECK_CUDA(cudaFuncSetAttribute(block_grad_umma_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  dim3 grid(n_blocks, gp.splits);
+  block_grad_umma_kernel<B><<<grid, kGemmThreads, C::SMEM_BYTES, st>>>(mx, mdy, gp);
+  SMT_CHECK_LAUNCH();
+  return SMT_OK;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+}  // namespace smt
+
+using namespace smt;
+
+extern "C" SMT_API int smt_block_grad_gemm_plan(int n_blocks, int block, int64_t T, int in_dtype, int* splits_host,
+                                        int* ctas_host) {
+  SMT_CHECK_ARG(block_ok(block), "smt_block_grad_gemm_plan: block size %d not in {64,128,256}", block);
+  SMT_CHECK_ARG(n_blocks >= 0 && T >= 0, "smt_block_grad_gemm_plan: negative size");
+  int splits = 1, ctas = 0;
+  if (n_blocks > 0 && T > 0) {
+    if (in_dtype == SMT_F32) {
+      ctas = n_blocks * (block / 64) * (block / 64);
+    } else {
+      Plan pl = make_plan(n_blocks, T);
+      splits = pl.splits;
+      ctas = n_blocks * pl.splits;
+    }
+  }
+  if (splits_host) *splits_host = splits;
+  if (ctas_host) *ctas_host = ctas;
+  return SMT_OK;
+}
+
+extern "C" SMT_API size_t smt_block_grad_gemm_workspace_bytes(int n_blocks, int block, int64_t T, int in_dtype) {
+  if (n_blocks <= 0 || T <= 0 || !block_ok(block) || in_dtype == SMT_F32) return 0;
+  Plan pl = make_plan(n_blocks, T);
+  if (pl.splits <= 1) return 0;
+  return (size_t)n_blocks * pl.splits * block * block * sizeof(float);
+}
+
+extern "C" SMT_API int smt_block_grad_gemm(const void* x, int64_t ldx, int in_features, const void* dy, int64_t lddy,
+                                   int out_features, int64_t T, int in_dtype, const int32_t* block_rc,
+                                   int n_blocks, int block, void* G, int out_dtype, int accumulate,
+                                   void* workspace, size_t workspace_bytes, void* stream) {
+  SMT_CHECK_ARG(n_blocks >= 0 && T >= 0, "smt_block_grad_gemm: negative size");
+  if (n_blocks == 0) return SMT_OK;
+  SMT_CHECK_ARG(block_ok(block), "smt_block_grad_gemm: block size %d not in {64,128,256}", block);
+  SMT_CHECK_ARG(G && block_rc, "smt_block_grad_gemm: null pointer");
+  SMT_CHECK_ARG(in_dtype >= SMT_F32 && in_dtype <= SMT_F16 && out_dtype >= SMT_F32 && out_dtype <= SMT_F16,
+                "smt_block_grad_gemm: bad dtype");
+  SMT_CHECK_ARG(in_features > 0 && out_features > 0 && in_features % block == 0 && out_features % block == 0,
+                "smt_block_grad_gemm: features (%d in, %d out) must be multiples of block %d", in_features,
+                out_features, block);
+  SMT_CHECK_ARG(aligned16(G), "smt_block_grad_gemm: G must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n_out = (int64_t)n_blocks * block * block;
+  if (T == 0) {  // empty token range: the sum is zero
+    if (!accumulate) SMT_CHECK_CUDA(cudaMemsetAsync(G, 0, (size_t)n_out * dtype_bytes(out_dtype), st));
+    return SMT_OK;
+  }
+  SMT_CHECK_ARG(x && dy, "smt_block_grad_gemm: null pointer");
+  SMT_CHECK_ARG(ldx >= in_features && lddy >= out_features, "smt_block_grad_gemm: leading dimension too small");
+  const int in_bytes = dtype_bytes(in_dtype);
+  SMT_CHECK_ARG(aligned16(x) && aligned16(dy) && (ldx * in_bytes) % 16 == 0 && (lddy * in_bytes) % 16 == 0,
+                "smt_block_grad_gemm: x and dy must be 16-byte aligned (pointer and row pitch)");
+
+  if (in_dtype == SMT_F32) {
+    dim3 grid(n_blocks, (block / 64) * (block / 64));
+    const float* xf = reinterpret_cast<const float*>(x);
+    const float* dyf = reinterpret_cast<const float*>(dy);
+    if (out_dtype == SMT_F32) block_grad_f32_kernel<SMT_F32><<<grid, 256, 0, st>>>(xf, ldx, dyf, lddy, T, block_rc, block, G, accumulate);
+    else if (out_dtype == SMT_BF16) block_grad_f32_kernel<SMT_BF16><<<grid, 256, 0, st>>>(xf, ldx, dyf, lddy, T, block_rc, block, G, accumulate);
+    else block_grad_f32_kernel<SMT_F16><<<grid, 256, 0, st>>>(xf, ldx, dyf, lddy, T, block_rc, block, G, accumulate);
+    SMT_CHECK_LAUNCH();
+    return SMT_OK;
+  }
+
+  SMT_CHECK_ARG(T < (1ll << 31) - kKTile, "smt_block_grad_gemm: T too large");
+  Plan pl = make_plan(n_blocks, T);
+  SMT_CHECK_ARG(pl.splits <= 65535, "smt_block_grad_gemm: too many splits");
+  const size_t need = smt_block_grad_gemm_workspace_bytes(n_blocks, block, T, in_dtype);
+  if (need > 0 && (workspace == nullptr || workspace_bytes < need)) {
+    set_error("smt_block_grad_gemm: workspace too small (%zu < %zu)", workspace_bytes, need);
+    return SMT_ERR_WORKSPACE;
+  }
+  if (need > 0) SMT_CHECK_ARG(aligned16(workspace), "smt_block_grad_gemm: workspace must be 16-byte aligned");
+
+  CUtensorMap mx, mdy;
+  if (int rc = encode_operand_map(&mx, x, in_features, T, ldx, in_dtype)) return rc;
+  if (int rc = encode_operand_map(&mdy, dy, out_features, T, lddy, in_dtype)) return rc;
+
+  GemmParams gp;
+  gp.block_rc = block_rc;
+  gp.out = pl.splits == 1 ? G : workspace;
+  gp.splits = pl.splits;
+  gp.kt_total = pl.kt_total;
+  gp.kt_per_split = pl.kt_per_split;
+  gp.out_dtype = out_dtype;
+  gp.accumulate = accumulate;
+  gp.in_fmt = in_dtype == SMT_BF16 ? 1 : 0;
+
+  int rc;
+  if (block == 256) rc = launch_umma<256>(mx, mdy, gp, n_blocks, st);
+  else if (block == 128) rc = launch_umma<128>(mx, mdy, gp, n_blocks, st);
+  else rc = launch_umma<64>(mx, mdy, gp, n_blocks, st);
+  if (rc) return rc;
+
+  if (pl.splits > 1) {
+    const int64_t n_vec8 = n_out / 8;
+    int64_t want = (n_vec8 + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    const int grid = (int)(want < cap ? want : cap);
+    const float* ws = reinterpret_cast<const float*>(workspace);
+    const int64_t tile = (int64_t)block * block;
+    if (out_dtype == SMT_F32) splitk_reduce_kernel<SMT_F32><<<grid, 256, 0, st>>>(ws, G, tile, pl.splits, n_vec8, accumulate);
+    else if (out_dtype == SMT_BF16) splitk_reduce_kernel<SMT_BF16><<<grid, 256, 0, st>>>(ws, G, tile, pl.splits, n_vec8, accumulate);
+    else splitk_reduce_kernel<SMT_F16><<<grid, 256, 0, st>>>(ws, G, tile, pl.splits, n_vec8, accumulate);
+    SMT_CHECK_LAUNCH();
+  }
+  return SMT_OK;
+}

@@ -1,0 +1,252 @@
+"""Tensor-level wrappers over the C-ABI: one Python function per entry point of `include/smt_b200.h`.
+
+PyTorch is used for device memory and streams only; all arithmetic happens in libsmt_b200.so.
+Every function launches on the CURRENT CUDA stream of the tensors' device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import BlockRef, check, dtype_id, load, ptr, require_cuda, stream_ptr
+
+STRATEGY_IDS = _lib.STRATEGY_IDS
+
+
+def _st(t: torch.Tensor) -> int:
+    return stream_ptr(t.device)
+
+
+# ---- block tables --------------------------------------------------------------------------------
+
+def make_block_table(entries: Sequence[Tuple[torch.Tensor, int, int]], device) -> torch.Tensor:
+    """Device array of `smt_block_ref` for [(weight, block_row, block_col), ...] (uint8 tensor view)."""
+    n = len(entries)
+    arr = (BlockRef * max(n, 1))()
+    for i, (w, r, c) in enumerate(entries):
+        if w.dim() != 2 or w.stride(1) != 1:
+            raise _lib.SMTLibraryError("block table: weights must be 2-D with unit column stride")
+        arr[i].w_ptr = w.data_ptr()
+        arr[i].ldw = w.stride(0)
+        arr[i].row = int(r)
+        arr[i].col = int(c)
+    host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)[: n * C.sizeof(BlockRef)].clone()
+    return host.to(device)
+
+
+def make_block_rc(index_list: Sequence[Tuple[int, int]], device) -> torch.Tensor:
+    """Device int32 [n, 2] table of (block_row, block_col) — the reference's `index_list`."""
+    if len(index_list) == 0:
+        return torch.empty((0, 2), dtype=torch.int32, device=device)
+    return torch.tensor([[int(r), int(c)] for r, c in index_list], dtype=torch.int32, device=device)
+
+
+# ---- warm-up scoring -------------------------------------------------------------------------------
+
+def score_accumulate(acc: torch.Tensor, grad: torch.Tensor) -> None:
+    """acc += grad (fp32 accumulator, any supported grad dtype). fine_tune.py:724-765."""
+    require_cuda(acc, grad)
+    assert acc.dtype == torch.float32 and acc.is_contiguous() and grad.is_contiguous()
+    assert acc.numel() == grad.numel()
+    check(load().smt_score_accumulate(ptr(acc), ptr(grad), dtype_id(grad.dtype), grad.numel(), _st(acc)),
+          "smt_score_accumulate")
+
+
+def block_sum_accumulate(block_sums: torch.Tensor, grad: torch.Tensor, block: int) -> None:
+    """block_sums[R/b, C/b] += per-block signed sums of grad[R, C]."""
+    require_cuda(block_sums, grad)
+    assert grad.dim() == 2 and grad.stride(1) == 1 and block_sums.dtype == torch.float32
+    R, Cc = grad.shape
+    assert block_sums.is_contiguous() and block_sums.numel() == (R // block) * (Cc // block)
+    check(load().smt_block_sum_accumulate(ptr(block_sums), ptr(grad), dtype_id(grad.dtype), R, Cc,
+                                          grad.stride(0), block, _st(grad)), "smt_block_sum_accumulate")
+
+
+def block_sum_finalize(block_sums: torch.Tensor, block: int) -> torch.Tensor:
+    require_cuda(block_sums)
+    out = torch.empty_like(block_sums)
+    check(load().smt_block_sum_finalize(ptr(block_sums), ptr(out), block_sums.numel(), block, _st(out)),
+          "smt_block_sum_finalize")
+    return out
+
+
+def block_score_reduce(acc: torch.Tensor, block: int, strategy: str = "mean_abs",
+                       out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """scores[R/b, C/b] of an fp32 [R, C] matrix. smt_helper.py:55-78, 233-251."""
+    require_cuda(acc)
+    assert acc.dim() == 2 and acc.dtype == torch.float32 and acc.stride(1) == 1
+    if strategy not in STRATEGY_IDS:
+        raise _lib.SMTLibraryError(f"unknown calculate_strategy {strategy!r}")
+    R, Cc = acc.shape
+    if out is None:
+        out = torch.empty((R // block, Cc // block), dtype=torch.float32, device=acc.device)
+    check(load().smt_block_score_reduce(ptr(acc), R, Cc, acc.stride(0), block, STRATEGY_IDS[strategy],
+                                        ptr(out), _st(acc)), "smt_block_score_reduce")
+    return out
+
+
+def act_score_accumulate(acc: torch.Tensor, x: torch.Tensor) -> None:
+    """acc[S, C] += sum_b |x[b, S, C]|. fine_tune.py:649-678 (reduced over batch)."""
+    require_cuda(acc, x)
+    assert x.dim() == 3 and x.is_contiguous() and acc.is_contiguous() and acc.dtype == torch.float32
+    Bn, S, Cc = x.shape
+    assert tuple(acc.shape) == (S, Cc)
+    check(load().smt_act_score_accumulate(ptr(acc), ptr(x), dtype_id(x.dtype), Bn, S, Cc, _st(x)),
+          "smt_act_score_accumulate")
+
+
+def channel_score_reduce(acc: torch.Tensor, strategy: str = "mean_abs") -> torch.Tensor:
+    require_cuda(acc)
+    assert acc.dim() == 2 and acc.is_contiguous() and acc.dtype == torch.float32
+    if strategy not in STRATEGY_IDS:
+        raise _lib.SMTLibraryError(f"unknown calculate_strategy {strategy!r}")
+    S, Cc = acc.shape
+    out = torch.empty((Cc,), dtype=torch.float32, device=acc.device)
+    check(load().smt_channel_score_reduce(ptr(acc), S, Cc, STRATEGY_IDS[strategy], ptr(out), _st(acc)),
+          "smt_channel_score_reduce")
+    return out
+
+
+# ---- top-k -----------------------------------------------------------------------------------------
+
+def topk_blocks(scores: torch.Tensor, seg_offsets: Sequence[int], seg_k: Sequence[int],
+                tiebreak_rank: Optional[torch.Tensor] = None,
+                inv_rank: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, list]:
+    """Segmented top-k. Returns (flat int32 indices on device, per-segment output offsets (host list))."""
+    require_cuda(scores, tiebreak_rank, inv_rank)
+    assert scores.dtype == torch.float32 and scores.is_contiguous()
+    n = scores.numel()
+    nseg = len(seg_k)
+    assert len(seg_offsets) == nseg + 1 and seg_offsets[-1] == n
+    out_offsets = [0]
+    for s in range(nseg):
+        length = seg_offsets[s + 1] - seg_offsets[s]
+        out_offsets.append(out_offsets[-1] + max(0, min(int(seg_k[s]), length)))
+    dev = scores.device
+    d_off = torch.tensor(list(seg_offsets), dtype=torch.int32, device=dev)
+    d_k = torch.tensor([int(k) for k in seg_k], dtype=torch.int32, device=dev)
+    d_out_off = torch.tensor(out_offsets, dtype=torch.int32, device=dev)
+    out = torch.empty((max(out_offsets[-1], 1),), dtype=torch.int32, device=dev)
+    lib = load()
+    ws_bytes = lib.smt_topk_workspace_bytes(n)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    if tiebreak_rank is not None:
+        assert tiebreak_rank.dtype == torch.int32 or tiebreak_rank.dtype == torch.uint32
+        assert inv_rank is not None and inv_rank.numel() == n and tiebreak_rank.numel() == n
+    check(lib.smt_topk_blocks(ptr(scores), ptr(tiebreak_rank), ptr(inv_rank), n, ptr(d_off), ptr(d_k),
+                              ptr(d_out_off), nseg, ptr(out), ptr(ws), ws_bytes, _st(scores)),
+          "smt_topk_blocks")
+    return out[: out_offsets[-1]], out_offsets
+
+
+# ---- gather / scatter ---------------------------------------------------------------------------------
+
+def block_gather(table: torch.Tensor, n_blocks: int, block: int, compact: torch.Tensor) -> None:
+    """compact[i] <- W_i block. smt.py:317-325."""
+    require_cuda(table, compact)
+    assert compact.is_contiguous() and compact.numel() == n_blocks * block * block
+    check(load().smt_block_gather(ptr(table), n_blocks, block, compact.element_size(), ptr(compact),
+                                  _st(compact)), "smt_block_gather")
+
+
+def block_scatter(table: torch.Tensor, n_blocks: int, block: int, compact: torch.Tensor) -> None:
+    """W_i block <- compact[i]. smt.py:332-341."""
+    require_cuda(table, compact)
+    assert compact.is_contiguous() and compact.numel() == n_blocks * block * block
+    check(load().smt_block_scatter(ptr(table), n_blocks, block, compact.element_size(), ptr(compact),
+                                   _st(compact)), "smt_block_scatter")
+
+
+# ---- block-gradient GEMM --------------------------------------------------------------------------------
+
+_ws_cache: dict = {}
+
+
+def _workspace(nbytes: int, device) -> Optional[torch.Tensor]:
+    """Grow-only per-(device, stream) scratch buffer (allocation stays out of the C library)."""
+    if nbytes == 0:
+        return None
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty((nbytes,), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def block_grad_gemm(x2d: torch.Tensor, dy2d: torch.Tensor, block_rc: torch.Tensor, block: int,
+                    out: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None,
+                    accumulate: bool = False) -> torch.Tensor:
+    """G[i*b+o, k] (+)= sum_t dy[t, r_i*b+o] * x[t, c_i*b+k]. smt.py:386-404.
+
+    x2d: [T, in], dy2d: [T, out] (unit column stride, same dtype); block_rc: int32 [n, 2] on device.
+    """
+    require_cuda(x2d, dy2d, block_rc)
+    assert x2d.dim() == 2 and dy2d.dim() == 2 and x2d.shape[0] == dy2d.shape[0]
+    assert x2d.stride(1) == 1 and dy2d.stride(1) == 1 and x2d.dtype == dy2d.dtype
+    assert block_rc.dtype == torch.int32 and block_rc.is_contiguous()
+    n = block_rc.shape[0]
+    T = x2d.shape[0]
+    if out is None:
+        out = torch.empty((n * block, block), dtype=out_dtype or dy2d.dtype, device=x2d.device)
+        accumulate = False
+    assert out.is_contiguous() and out.numel() == n * block * block
+    lib = load()
+    in_id = dtype_id(x2d.dtype)
+    ws_bytes = lib.smt_block_grad_gemm_workspace_bytes(n, block, T, in_id)
+    ws = _workspace(ws_bytes, x2d.device)
+    check(lib.smt_block_grad_gemm(ptr(x2d), x2d.stride(0) if T > 0 else x2d.shape[1], x2d.shape[1],
+                                  ptr(dy2d), dy2d.stride(0) if T > 0 else dy2d.shape[1], dy2d.shape[1],
+                                  T, in_id, ptr(block_rc), n, block, ptr(out), dtype_id(out.dtype),
+                                  1 if accumulate else 0, ptr(ws), ws_bytes, _st(x2d)),
+          "smt_block_grad_gemm")
+    return out
+
+
+def block_grad_gemm_plan(n_blocks: int, block: int, T: int, dtype: torch.dtype) -> Tuple[int, int]:
+    a, b = C.c_int(), C.c_int()
+    check(load().smt_block_grad_gemm_plan(n_blocks, block, T, dtype_id(dtype), C.byref(a), C.byref(b)),
+          "smt_block_grad_gemm_plan")
+    return a.value, b.value
+
+
+# ---- optimizer ---------------------------------------------------------------------------------------------
+
+def grad_sqnorm(grad: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Deterministic sum of squares of a flat gradient buffer -> fp32 scalar tensor on device."""
+    require_cuda(grad)
+    assert grad.is_contiguous()
+    if out is None:
+        out = torch.empty((1,), dtype=torch.float32, device=grad.device)
+    lib = load()
+    ws_bytes = lib.smt_grad_sqnorm_workspace_bytes()
+    ws = _workspace(ws_bytes, grad.device)
+    check(lib.smt_grad_sqnorm(ptr(grad), dtype_id(grad.dtype), grad.numel(), ptr(out), ptr(ws), ws_bytes,
+                              _st(grad)), "smt_grad_sqnorm")
+    return out
+
+
+def compact_adam(master: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.Tensor, grad: torch.Tensor,
+                 *, lr: float, beta1: float, beta2: float, eps: float, weight_decay: float, step: int,
+                 grad_scale: float = 1.0, sqnorm: Optional[torch.Tensor] = None, max_norm: float = 0.0,
+                 compact_out: Optional[torch.Tensor] = None, table: Optional[torch.Tensor] = None,
+                 n_blocks: int = 0, block: int = 0, w_dtype: Optional[torch.dtype] = None) -> None:
+    """One fused AdamW step over flat compact state (+ clip, + dense write-back). See smt_b200.h."""
+    require_cuda(master, exp_avg, exp_avg_sq, grad, sqnorm, compact_out, table)
+    for t in (master, exp_avg, exp_avg_sq):
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == grad.numel()
+    assert grad.is_contiguous()
+    bc1 = 1.0 - beta1 ** step
+    bc2 = 1.0 - beta2 ** step
+    check(load().smt_compact_adam(
+        ptr(master), ptr(exp_avg), ptr(exp_avg_sq), ptr(grad), dtype_id(grad.dtype), grad.numel(),
+        lr, beta1, beta2, eps, weight_decay, bc1, bc2, grad_scale, ptr(sqnorm), max_norm,
+        ptr(compact_out), dtype_id(compact_out.dtype) if compact_out is not None else BF16_ID,
+        ptr(table), n_blocks, block, dtype_id(w_dtype) if w_dtype is not None else BF16_ID, _st(master)),
+        "smt_compact_adam")
+
+
+BF16_ID = _lib.BF16
