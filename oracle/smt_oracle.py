@@ -74,6 +74,9 @@ def select_from_scores(block_means: dict, n: int, selection_strategy: str = "no_
     heap.sort(reverse=True)                                # smt_helper.py:129-130
     for _score, (key, i, j) in heap:                       # smt_helper.py:138-139
         ranked[key].append((i, j))
+    if not heap:
+        # smt_helper.py:141-142: `del mean` / `del info` after a loop that never ran (n <= 0 or no blocks)
+        raise UnboundLocalError("cannot access local variable 'mean' where it is not associated with a value")
     return ranked
 
 
@@ -278,3 +281,38 @@ def adamw_fused_step(p, m, v, g, *, lr, beta1, beta2, eps, weight_decay, step, g
     update = (m / bc1) / denom + f(weight_decay) * p
     p = p - f(lr) * update
     return p.astype(np.float32), m.astype(np.float32), v.astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU modules restating LinearLayer_MatrixSparsity / linearZ — used by bench.py's CPU-baseline legs only
+# ------------------------------------------------------------------------------------------------------
+
+class OracleLinearZ(torch.autograd.Function):
+    """linearZ, smt.py:347-413, restated on top of linearz_forward / linearz_backward above."""
+
+    @staticmethod
+    def forward(ctx, input, selected_weight, matrix_index_list, weight, block):
+        ctx.index_list, ctx.block = matrix_index_list, block
+        ctx.save_for_backward(input, weight)
+        return linearz_forward(input, weight)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        x, weight = ctx.saved_tensors
+        gi, gw = linearz_backward(x, grad_output, weight, ctx.index_list, ctx.block)
+        return gi, gw, None, None, None
+
+
+class OracleSparseLinear(torch.nn.Module):
+    """LinearLayer_MatrixSparsity, smt.py:302-344: gather at construction, scatter at every forward."""
+
+    def __init__(self, weight, index_list, block: int = BLOCK):
+        super().__init__()
+        self.weight = weight
+        self.weight.requires_grad = False
+        self.index_list, self.block = index_list, block
+        self.selected_weight = torch.nn.Parameter(gather_blocks(weight.data, index_list, block))
+
+    def forward(self, x):
+        scatter_blocks(self.weight.data, self.selected_weight.data, self.index_list, self.block)   # smt.py:332-341
+        return OracleLinearZ.apply(x, self.selected_weight, self.index_list, self.weight, self.block)

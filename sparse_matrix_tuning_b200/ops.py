@@ -15,6 +15,51 @@ from ._lib import BlockRef, check, dtype_id, load, ptr, require_cuda, stream_ptr
 
 STRATEGY_IDS = _lib.STRATEGY_IDS
 
+# ---- instrumentation (bench.py): number of OUR kernels launched, optional CUDA-event timing of one op -------
+LAUNCHES = {"total": 0}
+_timers: dict = {}
+
+
+def _count(n: int = 1) -> None:
+    LAUNCHES["total"] += n
+
+
+def enable_timing(op_name: str, enabled: bool = True) -> None:
+    """Bracket every call of `op_name` ('block_grad_gemm', 'compact_adam', ...) with CUDA events recorded on the
+    launching stream; read the durations with `collect_timing` after a synchronize."""
+    if enabled:
+        _timers[op_name] = []
+    else:
+        _timers.pop(op_name, None)
+
+
+def collect_timing(op_name: str, reset: bool = True):
+    """[(milliseconds, tag), ...] for the bracketed calls since the last reset (synchronizes the events)."""
+    rec = _timers.get(op_name, [])
+    out = [(a.elapsed_time(b), tag) for a, b, tag in rec]
+    if reset and op_name in _timers:
+        _timers[op_name] = []
+    return out
+
+
+class _timed:
+    def __init__(self, op_name, device, tag=None):
+        self.rec = _timers.get(op_name)
+        self.device, self.tag = device, tag
+
+    def __enter__(self):
+        if self.rec is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record(torch.cuda.current_stream(self.device))
+        return self
+
+    def __exit__(self, *exc):
+        if self.rec is not None:
+            self.b.record(torch.cuda.current_stream(self.device))
+            self.rec.append((self.a, self.b, self.tag))
+        return False
+
 
 def _st(t: torch.Tensor) -> int:
     return stream_ptr(t.device)
@@ -53,6 +98,7 @@ def score_accumulate(acc: torch.Tensor, grad: torch.Tensor) -> None:
     assert acc.numel() == grad.numel()
     check(load().smt_score_accumulate(ptr(acc), ptr(grad), dtype_id(grad.dtype), grad.numel(), _st(acc)),
           "smt_score_accumulate")
+    _count()
 
 
 def block_sum_accumulate(block_sums: torch.Tensor, grad: torch.Tensor, block: int) -> None:
@@ -63,6 +109,7 @@ def block_sum_accumulate(block_sums: torch.Tensor, grad: torch.Tensor, block: in
     assert block_sums.is_contiguous() and block_sums.numel() == (R // block) * (Cc // block)
     check(load().smt_block_sum_accumulate(ptr(block_sums), ptr(grad), dtype_id(grad.dtype), R, Cc,
                                           grad.stride(0), block, _st(grad)), "smt_block_sum_accumulate")
+    _count()
 
 
 def block_sum_finalize(block_sums: torch.Tensor, block: int) -> torch.Tensor:
@@ -70,6 +117,7 @@ def block_sum_finalize(block_sums: torch.Tensor, block: int) -> torch.Tensor:
     out = torch.empty_like(block_sums)
     check(load().smt_block_sum_finalize(ptr(block_sums), ptr(out), block_sums.numel(), block, _st(out)),
           "smt_block_sum_finalize")
+    _count()
     return out
 
 
@@ -85,6 +133,7 @@ def block_score_reduce(acc: torch.Tensor, block: int, strategy: str = "mean_abs"
         out = torch.empty((R // block, Cc // block), dtype=torch.float32, device=acc.device)
     check(load().smt_block_score_reduce(ptr(acc), R, Cc, acc.stride(0), block, STRATEGY_IDS[strategy],
                                         ptr(out), _st(acc)), "smt_block_score_reduce")
+    _count()
     return out
 
 
@@ -96,6 +145,7 @@ def act_score_accumulate(acc: torch.Tensor, x: torch.Tensor) -> None:
     assert tuple(acc.shape) == (S, Cc)
     check(load().smt_act_score_accumulate(ptr(acc), ptr(x), dtype_id(x.dtype), Bn, S, Cc, _st(x)),
           "smt_act_score_accumulate")
+    _count()
 
 
 def channel_score_reduce(acc: torch.Tensor, strategy: str = "mean_abs") -> torch.Tensor:
@@ -107,6 +157,7 @@ def channel_score_reduce(acc: torch.Tensor, strategy: str = "mean_abs") -> torch
     out = torch.empty((Cc,), dtype=torch.float32, device=acc.device)
     check(load().smt_channel_score_reduce(ptr(acc), S, Cc, STRATEGY_IDS[strategy], ptr(out), _st(acc)),
           "smt_channel_score_reduce")
+    _count()
     return out
 
 
@@ -139,6 +190,7 @@ def topk_blocks(scores: torch.Tensor, seg_offsets: Sequence[int], seg_k: Sequenc
     check(lib.smt_topk_blocks(ptr(scores), ptr(tiebreak_rank), ptr(inv_rank), n, ptr(d_off), ptr(d_k),
                               ptr(d_out_off), nseg, ptr(out), ptr(ws), ws_bytes, _st(scores)),
           "smt_topk_blocks")
+    _count()
     return out[: out_offsets[-1]], out_offsets
 
 
@@ -150,6 +202,7 @@ def block_gather(table: torch.Tensor, n_blocks: int, block: int, compact: torch.
     assert compact.is_contiguous() and compact.numel() == n_blocks * block * block
     check(load().smt_block_gather(ptr(table), n_blocks, block, compact.element_size(), ptr(compact),
                                   _st(compact)), "smt_block_gather")
+    _count()
 
 
 def block_scatter(table: torch.Tensor, n_blocks: int, block: int, compact: torch.Tensor) -> None:
@@ -158,6 +211,7 @@ def block_scatter(table: torch.Tensor, n_blocks: int, block: int, compact: torch
     assert compact.is_contiguous() and compact.numel() == n_blocks * block * block
     check(load().smt_block_scatter(ptr(table), n_blocks, block, compact.element_size(), ptr(compact),
                                    _st(compact)), "smt_block_scatter")
+    _count()
 
 
 # ---- block-gradient GEMM --------------------------------------------------------------------------------
@@ -198,11 +252,14 @@ def block_grad_gemm(x2d: torch.Tensor, dy2d: torch.Tensor, block_rc: torch.Tenso
     in_id = dtype_id(x2d.dtype)
     ws_bytes = lib.smt_block_grad_gemm_workspace_bytes(n, block, T, in_id)
     ws = _workspace(ws_bytes, x2d.device)
-    check(lib.smt_block_grad_gemm(ptr(x2d), x2d.stride(0) if T > 0 else x2d.shape[1], x2d.shape[1],
-                                  ptr(dy2d), dy2d.stride(0) if T > 0 else dy2d.shape[1], dy2d.shape[1],
-                                  T, in_id, ptr(block_rc), n, block, ptr(out), dtype_id(out.dtype),
-                                  1 if accumulate else 0, ptr(ws), ws_bytes, _st(x2d)),
-          "smt_block_grad_gemm")
+    with _timed("block_grad_gemm", x2d.device, (n, block, T)):
+        check(lib.smt_block_grad_gemm(ptr(x2d), x2d.stride(0) if T > 0 else x2d.shape[1], x2d.shape[1],
+                                      ptr(dy2d), dy2d.stride(0) if T > 0 else dy2d.shape[1], dy2d.shape[1],
+                                      T, in_id, ptr(block_rc), n, block, ptr(out), dtype_id(out.dtype),
+                                      1 if accumulate else 0, ptr(ws), ws_bytes, _st(x2d)),
+              "smt_block_grad_gemm")
+    if n > 0 and T > 0:
+        _count(2 if ws_bytes > 0 else 1)
     return out
 
 
@@ -226,6 +283,7 @@ def grad_sqnorm(grad: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch
     ws = _workspace(ws_bytes, grad.device)
     check(lib.smt_grad_sqnorm(ptr(grad), dtype_id(grad.dtype), grad.numel(), ptr(out), ptr(ws), ws_bytes,
                               _st(grad)), "smt_grad_sqnorm")
+    _count(2)
     return out
 
 
@@ -241,7 +299,9 @@ def compact_adam(master: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.
     assert grad.is_contiguous()
     bc1 = 1.0 - beta1 ** step
     bc2 = 1.0 - beta2 ** step
-    check(load().smt_compact_adam(
+    _count()
+    with _timed("compact_adam", master.device, grad.numel()):
+      check(load().smt_compact_adam(
         ptr(master), ptr(exp_avg), ptr(exp_avg_sq), ptr(grad), dtype_id(grad.dtype), grad.numel(),
         lr, beta1, beta2, eps, weight_decay, bc1, bc2, grad_scale, ptr(sqnorm), max_norm,
         ptr(compact_out), dtype_id(compact_out.dtype) if compact_out is not None else BF16_ID,

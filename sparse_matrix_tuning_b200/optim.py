@@ -1,0 +1,248 @@
+"""`SMTAdam`: the compact AdamW step of the SMT phase as ONE fused sm_100a kernel per parameter group.
+
+Reference call sites replaced (paths relative to the reference root):
+  deepspeed/fine_tune.py:352-363   `FusedAdam(optimizer_grouped_parameters, lr=ft_learning_rate, betas=(0.9, 0.95))`
+  deepspeed/fine_tune.py:379-384   `deepspeed.initialize(... optimizer=new_optimizer ...)` — bf16 params with fp32
+                                   masters and `gradient_clipping: 1.0` (helpers/deepspeed_helpers.py:87)
+  deepspeed/fine_tune.py:773       `model.step()`
+  deepspeed/smt/smt.py:332-341     the per-forward scatter of the updated blocks into the dense weight
+
+The constructor accepts FusedAdam's keyword arguments, so the driver line at fine_tune.py:352 works unchanged
+with `AdamOptimizer = SMTAdam`.  It is a regular `torch.optim.Optimizer` (param_groups, state_dict, LR
+schedulers work).
+
+Memory layout (`flatten=True`, the default): each parameter group becomes one flat arena — `flat_param` and
+`flat_grad` in the parameter dtype, fp32 `master` / `exp_avg` / `exp_avg_sq` — and every parameter's `.data`
+and `.grad` are re-pointed to views of it.  `flat_grad` is therefore the single buffer a data-parallel step
+all-reduces (see dp.py), and `linearZ.backward` writes block gradients straight into it.  One `smt_grad_sqnorm`
++ one `smt_compact_adam` launch per group then performs: optional 1/world scaling, global-norm clip, AdamW on the
+fp32 masters, rounding to the parameter dtype into `flat_param`, and the write-back of every updated block into
+its dense weight matrix.
+"""
+from __future__ import annotations
+
+import weakref
+from typing import List, Optional
+
+import torch
+
+from . import ops
+from ._lib import SMTLibraryError
+
+
+def _owner_of(p):
+    ref = getattr(p, "_smt_owner", None)
+    return ref() if ref is not None else None
+
+
+class _Arena:
+    """Flat storage of one parameter group."""
+
+    def __init__(self, params: List[torch.nn.Parameter]):
+        first = params[0]
+        self.params = params
+        self.device = first.device
+        self.dtype = first.dtype
+        offs, total = [], 0
+        for p in params:
+            if p.device != self.device or p.dtype != self.dtype:
+                raise SMTLibraryError("SMTAdam: all parameters of a group must share device and dtype")
+            offs.append(total)
+            total += (p.numel() + 7) // 8 * 8              # kernels work on 8-element vectors
+        self.offsets, self.total = offs, total
+        self.flat_param = torch.zeros(total, dtype=self.dtype, device=self.device)
+        self.flat_grad = torch.zeros(total, dtype=self.dtype, device=self.device)
+        self.master = torch.zeros(total, dtype=torch.float32, device=self.device)
+        self.exp_avg = torch.zeros(total, dtype=torch.float32, device=self.device)
+        self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=self.device)
+        self.sqnorm = torch.zeros(1, dtype=torch.float32, device=self.device)
+        for p, off in zip(params, offs):
+            n = p.numel()
+            view = self.flat_param[off:off + n].view(p.shape)
+            view.copy_(p.data)
+            self.master[off:off + n].copy_(p.data.reshape(-1).float())
+            p.data = view
+            g = self.flat_grad[off:off + n].view(p.shape)
+            if p.grad is not None:
+                g.copy_(p.grad)
+            p.grad = g
+            if _owner_of(p) is not None:
+                p._smt_grad_sink = g                       # linearZ.backward accumulates here directly
+        self._table = None
+        self._table_key = None
+
+    def fused_table(self):
+        """One block table covering the whole arena, or None when the group is not purely SMT blocks of one
+        block size / weight dtype (then the step falls back to per-parameter launches)."""
+        owners = [_owner_of(p) for p in self.params]
+        if any(o is None for o in owners):
+            return None
+        blocks = {o.block for o in owners}
+        wdt = {o.weight.dtype for o in owners}
+        if len(blocks) != 1 or len(wdt) != 1:
+            return None
+        key = tuple((o.weight.data_ptr(), o.weight.stride(0)) for o in owners)
+        if self._table is None or self._table_key != key:
+            entries = []
+            for o in owners:
+                entries += [(o.weight.data, r, c) for r, c in o.index_list]
+            self._table = (ops.make_block_table(entries, self.device), len(entries), blocks.pop(), wdt.pop())
+            self._table_key = key
+        return self._table
+
+
+class SMTAdam(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, bias_correction=True, betas=(0.9, 0.999), eps=1e-8, adam_w_mode=True,
+                 weight_decay=0.0, amsgrad=False, set_grad_none=False, max_grad_norm=0.0, flatten=True,
+                 grad_scale=1.0):
+        if amsgrad:
+            raise SMTLibraryError("SMTAdam: amsgrad is not supported (neither does FusedAdam)")
+        if not adam_w_mode or not bias_correction:
+            raise SMTLibraryError("SMTAdam implements FusedAdam's default adam_w_mode with bias correction only")
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        super().__init__(params, defaults)
+        self.max_grad_norm = float(max_grad_norm)
+        self.grad_scale = float(grad_scale)                # e.g. 1/world_size after a SUM all-reduce
+        self.flatten = bool(flatten)
+        self._arenas: List[Optional[_Arena]] = []
+        for group in self.param_groups:
+            group.setdefault("step", 0)
+            ps = [p for p in group["params"] if p.requires_grad]
+            for p in ps:
+                if not p.is_cuda:
+                    raise SMTLibraryError("SMTAdam: parameters must live on a CUDA device (no CPU fallback)")
+            self._arenas.append(_Arena(ps) if (self.flatten and ps) else None)
+        self._publish_state()
+
+    # -- introspection ---------------------------------------------------------------------------------
+    def flat_grads(self) -> List[torch.Tensor]:
+        """The flat gradient buffers (one per non-empty group) — what a data-parallel step all-reduces."""
+        return [a.flat_grad for a in self._arenas if a is not None]
+
+    def trainable_elements(self) -> int:
+        return sum(p.numel() for g in self.param_groups for p in g["params"] if p.requires_grad)
+
+    def _publish_state(self) -> None:
+        # expose per-parameter views so torch's state_dict()/schedulers see ordinary Adam state
+        for group, arena in zip(self.param_groups, self._arenas):
+            if arena is None:
+                continue
+            for p, off in zip(arena.params, arena.offsets):
+                n = p.numel()
+                self.state[p] = {"exp_avg": arena.exp_avg[off:off + n].view(p.shape),
+                                 "exp_avg_sq": arena.exp_avg_sq[off:off + n].view(p.shape),
+                                 "master": arena.master[off:off + n].view(p.shape)}
+
+    def load_state_dict(self, state_dict):
+        views = {id(p): dict(self.state[p]) for p in self.state}
+        super().load_state_dict(state_dict)
+        # copy the loaded tensors back INTO the arena views (super() replaced them by fresh tensors)
+        for group in self.param_groups:
+            for p in group["params"]:
+                if id(p) in views and p in self.state:
+                    loaded = self.state[p]
+                    for name, view in views[id(p)].items():
+                        if name in loaded and torch.is_tensor(loaded[name]):
+                            view.copy_(loaded[name])
+                    self.state[p] = views[id(p)]
+
+    def zero_grad(self, set_to_none: bool = False):
+        """Zeroes the flat gradient buffers in place (the views stay attached, so nothing is re-pointed)."""
+        for group, arena in zip(self.param_groups, self._arenas):
+            if arena is not None:
+                arena.flat_grad.zero_()
+            else:
+                for p in group["params"]:
+                    if p.grad is not None:
+                        if set_to_none:
+                            p.grad = None
+                        else:
+                            p.grad.zero_()
+
+    # -- the step --------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        clip = self.max_grad_norm > 0.0
+        total_sq = None
+        if clip:
+            parts = []
+            for group, arena in zip(self.param_groups, self._arenas):
+                if arena is not None:
+                    parts.append(ops.grad_sqnorm(arena.flat_grad, arena.sqnorm))
+                else:
+                    parts += [ops.grad_sqnorm(p.grad.contiguous()) for p in group["params"] if p.grad is not None]
+            if len(parts) == 1:
+                total_sq = parts[0]
+            elif parts:
+                total_sq = torch.stack([t.reshape(()) for t in parts]).sum().reshape(1)
+        for group, arena in zip(self.param_groups, self._arenas):
+            group["step"] += 1
+            b1, b2 = group["betas"]
+            common = dict(lr=float(group["lr"]), beta1=float(b1), beta2=float(b2), eps=float(group["eps"]),
+                          weight_decay=float(group["weight_decay"]), step=int(group["step"]),
+                          grad_scale=self.grad_scale, sqnorm=total_sq, max_norm=self.max_grad_norm if clip else 0.0)
+            if arena is not None:
+                self._step_arena(arena, common)
+            else:
+                for p in group["params"]:
+                    if p.grad is not None:
+                        self._step_loose(p, common)
+        return loss
+
+    def _step_arena(self, arena: _Arena, common) -> None:
+        fused = arena.fused_table()
+        if fused is not None:
+            table, n_blocks, block, w_dtype = fused
+            ops.compact_adam(arena.master, arena.exp_avg, arena.exp_avg_sq, arena.flat_grad,
+                             compact_out=arena.flat_param, table=table, n_blocks=n_blocks, block=block,
+                             w_dtype=w_dtype, **common)
+            for p in arena.params:
+                _owner_of(p).mark_synced()
+            return
+        for p, off in zip(arena.params, arena.offsets):
+            n = (p.numel() + 7) // 8 * 8
+            sl = slice(off, off + n)
+            owner = _owner_of(p)
+            kw = dict(common)
+            if owner is not None and len(owner.index_list) * owner.block * owner.block == n:
+                kw.update(table=owner._block_table(), n_blocks=len(owner.index_list), block=owner.block,
+                          w_dtype=owner.weight.dtype)
+            ops.compact_adam(arena.master[sl], arena.exp_avg[sl], arena.exp_avg_sq[sl], arena.flat_grad[sl],
+                             compact_out=arena.flat_param[sl], **kw)
+            if owner is not None and "table" in kw:
+                owner.mark_synced()
+            else:
+                torch.autograd.graph.increment_version(p)   # forward() must re-scatter / autograd must notice
+
+    def _step_loose(self, p, common) -> None:
+        """Unflattened mode (e.g. under a wrapper that owns the flat buffers itself): per-parameter state."""
+        st = self.state[p]
+        n = p.numel()
+        if n % 8 != 0 or not p.data.is_contiguous():
+            raise SMTLibraryError("SMTAdam(flatten=False): parameters must be contiguous with numel % 8 == 0")
+        if "exp_avg" not in st:
+            st["exp_avg"] = torch.zeros(n, dtype=torch.float32, device=p.device)
+            st["exp_avg_sq"] = torch.zeros(n, dtype=torch.float32, device=p.device)
+            st["master"] = p.data.reshape(-1) if p.dtype == torch.float32 else p.data.reshape(-1).float()
+        g = p.grad.contiguous().reshape(-1)
+        out = None if p.dtype == torch.float32 else p.data.reshape(-1)
+        owner = _owner_of(p)
+        kw = dict(common)
+        if owner is not None:
+            kw.update(table=owner._block_table(), n_blocks=len(owner.index_list), block=owner.block,
+                      w_dtype=owner.weight.dtype)
+        ops.compact_adam(st["master"], st["exp_avg"], st["exp_avg_sq"], g, compact_out=out, **kw)
+        if owner is not None:
+            owner.mark_synced()
+        else:
+            torch.autograd.graph.increment_version(p)
+
+
+def register_owner(param: torch.nn.Parameter, module) -> None:
+    """Ties a `selected_weight` Parameter to its LinearLayer_MatrixSparsity (weakly) so the optimizer can
+    find the dense weight to write back into."""
+    param._smt_owner = weakref.ref(module)

@@ -1,0 +1,352 @@
+"""Drop-in mirror of the reference module `deepspeed/smt/smt.py`, backed by sm_100a kernels.
+
+Public names kept identical to what the reference driver imports (fine_tune.py:39):
+
+    LinearLayer_MatrixSparsity                smt.py:302-344
+    linearZ                                   smt.py:347-413
+    convert_linear_layer_to_matrix_sparsity   smt.py:83-179
+    convert_matrix_sparsity_to_linear_layer   smt.py:416-457
+    freeze_unselected_matrix_layer            smt.py:641-745
+    get_optimizer_sparse_grouped_parameters   smt.py:465-549
+    get_optimizer_qk_augment_grouped_parameters  smt.py:554-638
+    Block_dimension                           smt.py:22 (module global, read at call time)
+
+What changed underneath:
+  * `__init__` gathers all selected blocks with ONE kernel launch (`smt_block_gather`) instead of n slice copies;
+  * `forward` scatters compact -> dense with ONE launch and only when `selected_weight` changed since the last
+    scatter (the reference re-scatters n slices on every forward, twice per step under checkpointing);
+    when the fused optimizer (`SMTAdam`) wrote the blocks itself, nothing is launched at all;
+  * `linearZ.backward` forms every selected block gradient in ONE grouped tcgen05/TMEM GEMM
+    (`smt_block_grad_gemm`): fp32 accumulation over all B*S tokens, rounded once — the reference does a bmm, a
+    batch reduction and a slice copy per block, rounding to bf16 per batch entry;
+  * importing this module does not call `deepspeed.init_distributed()` (the reference does, smt.py:20).
+
+The channel-sparsity twins (`convert_linear_layer_to_channel_sparsity`, `freeze_unselected_channel_layer`) are
+importable but raise: the reference implementation selects rows and differentiates columns and fails for every
+non-square weight, so there is nothing well-defined to be compatible with.
+"""
+from __future__ import annotations
+
+import re
+import weakref
+from typing import Dict, List, Sequence, Tuple
+
+import torch
+from torch import nn
+
+from .. import ops
+from .._lib import SMTLibraryError
+
+Block_dimension = 256
+
+_LAYER_RE = re.compile(r"model\.layers\.(\d+)\.")
+_MLP_NAMES = ("gate_proj", "up_proj", "down_proj")
+_ATTN_NAMES = ("q_proj", "k_proj", "v_proj", "o_proj")
+
+
+def _rank0_print(msg: str) -> None:
+    if not torch.distributed.is_available() or not torch.distributed.is_initialized() \
+            or torch.distributed.get_rank() == 0:
+        print(msg)
+
+
+def _getattr_path(root, dotted: str):
+    obj = root
+    for part in dotted.split("."):
+        obj = getattr(obj, part)
+    return obj
+
+
+def _setattr_path(root, dotted: str, value) -> None:
+    parts = dotted.split(".")
+    obj = root
+    for part in parts[:-1]:
+        obj = getattr(obj, part)
+    setattr(obj, parts[-1], value)
+
+
+def _layer_of(name: str):
+    m = _LAYER_RE.search(name)
+    return int(m.group(1)) if m else None
+
+
+def _mlp_kind(name: str) -> str:
+    # smt.py:104 — anything that is not gate/up falls through to 'down_proj'
+    return "gate_proj" if "gate_proj" in name else "up_proj" if "up_proj" in name else "down_proj"
+
+
+def _attn_kind(name: str):
+    # smt.py:120 — q, k, v, o by substring, else None
+    for kind in _ATTN_NAMES:
+        if kind in name:
+            return kind
+    return None
+
+
+# ---- device-side index tables ---------------------------------------------------------------------------
+
+_rc_cache: Dict[Tuple[int, torch.device], Tuple[tuple, torch.Tensor]] = {}
+
+
+def _block_rc_for(index_list, device) -> torch.Tensor:
+    """int32 [n, 2] device copy of a Python index list, cached per list object and validated by value
+    (linearZ receives only the plain list, exactly like the reference)."""
+    snap = tuple((int(r), int(c)) for r, c in index_list)
+    key = (id(index_list), device)
+    hit = _rc_cache.get(key)
+    if hit is not None and hit[0] == snap:
+        return hit[1]
+    t = ops.make_block_rc(snap, device)
+    if len(_rc_cache) > 4096:
+        _rc_cache.clear()
+    _rc_cache[key] = (snap, t)
+    return t
+
+
+class linearZ(torch.autograd.Function):
+    """y = x W^T with a block-sparse weight gradient.  Reference: smt.py:347-413.
+
+    forward(ctx, input, selected_weight, matrix_index_list, weight)
+    backward -> (grad_input, grad_weight [n*b, b], None, None)
+    """
+
+    @staticmethod
+    def forward(ctx, input, selected_weight, matrix_index_list, weight):
+        ctx.block = Block_dimension
+        ctx.index_list = matrix_index_list
+        ctx.sw_ref = selected_weight                      # only for the optional gradient sink (no data use)
+        ctx.save_for_backward(input, weight)              # the reference keeps column views of `input` alive
+        return torch.matmul(input, weight.t())            # smt.py:366 (dense, cuBLAS)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        x, weight = ctx.saved_tensors
+        b = ctx.block
+        grad_input = grad_weight = None
+        if ctx.needs_input_grad[1]:
+            n = len(ctx.index_list)
+            x2 = x.reshape(-1, x.shape[-1])
+            dy2 = grad_output.reshape(-1, grad_output.shape[-1])
+            if dy2.stride(-1) != 1 or (dy2.stride(0) * dy2.element_size()) % 16 != 0:
+                dy2 = dy2.contiguous()
+            if x2.stride(-1) != 1 or (x2.stride(0) * x2.element_size()) % 16 != 0:
+                x2 = x2.contiguous()
+            if x2.dtype != dy2.dtype:
+                x2 = x2.to(dy2.dtype)
+            rc = _block_rc_for(ctx.index_list, dy2.device)
+            sink = getattr(ctx.sw_ref, "_smt_grad_sink", None)
+            if sink is not None:
+                # native mode: accumulate straight into the flat (NCCL) gradient buffer, nothing returned
+                ops.block_grad_gemm(x2, dy2, rc, b, out=sink, accumulate=True)
+            else:
+                grad_weight = ops.block_grad_gemm(x2, dy2, rc, b, out_dtype=grad_output.dtype)  # smt.py:382-404
+                grad_weight = grad_weight.view(n * b, b)
+        if ctx.needs_input_grad[0]:
+            grad_input = torch.matmul(grad_output, weight)                                      # smt.py:406
+        return grad_input, grad_weight, None, None
+
+
+class LinearLayer_MatrixSparsity(nn.Module):
+    """Linear layer whose only trainable parameter is a compact copy of its selected b x b blocks.
+    Reference: smt.py:302-344 (same constructor signature and attribute names)."""
+
+    def __init__(self, weight, bias=None, index_list=[]):
+        super().__init__()
+        if not weight.is_cuda:
+            raise SMTLibraryError("LinearLayer_MatrixSparsity needs its weight on a CUDA device: the SMT kernels "
+                                  "have no CPU fallback")
+        b = Block_dimension
+        self.weight = weight
+        self.weight.requires_grad = False                 # smt.py:308
+        self.bias = bias                                  # kept but unused, exactly like smt.py:309,343
+        self.index_list = index_list
+        self.block = b
+        for (r, c) in index_list:
+            if not (0 <= r < weight.shape[0] // b and 0 <= c < weight.shape[1] // b):
+                raise IndexError(f"block ({r}, {c}) outside a {tuple(weight.shape)} weight with block {b}")
+        n = len(index_list)
+        compact = torch.empty(n * b, b, dtype=weight.dtype, device=weight.device)
+        self._table = None
+        self._table_key = None
+        if n:
+            ops.block_gather(self._block_table(), n, b, compact)       # smt.py:317-325
+        self.selected_weight = nn.Parameter(compact, requires_grad=True)
+        self.selected_weight._smt_owner = weakref.ref(self)   # lets SMTAdam find the dense weight to write back
+        self.fn = linearZ.apply
+        # (storage pointer, version) of selected_weight at the last compact -> dense write-back
+        self._synced = (self.selected_weight.data_ptr(), self.selected_weight._version)
+
+    # -- device table of (W pointer, ld, row, col) per block, rebuilt if the weight storage moves --
+    def _block_table(self) -> torch.Tensor:
+        w = self.weight.data
+        key = (w.data_ptr(), w.stride(0), w.device)
+        if self._table is None or self._table_key != key:
+            self._table = ops.make_block_table([(w, r, c) for r, c in self.index_list], w.device)
+            self._table_key = key
+        return self._table
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self._table = None
+        self._synced = None
+        return out
+
+    def mark_synced(self) -> None:
+        """Called by the fused optimizer after it has written the updated blocks into `weight` itself."""
+        self._synced = (self.selected_weight.data_ptr(), self.selected_weight._version)
+
+    def sync_weight(self, force: bool = False) -> None:
+        """compact -> dense write-back (smt.py:332-341) — one launch, skipped when nothing changed."""
+        state = (self.selected_weight.data_ptr(), self.selected_weight._version)
+        if force or self._synced != state:
+            n = len(self.index_list)
+            if n:
+                sw = self.selected_weight.data
+                if sw.dtype != self.weight.dtype:
+                    sw = sw.to(self.weight.dtype)
+                ops.block_scatter(self._block_table(), n, self.block, sw.contiguous())
+            self._synced = state
+
+    def forward(self, x):
+        self.sync_weight()
+        return self.fn(x, self.selected_weight, self.index_list, self.weight)   # smt.py:343
+
+
+# ---- model surgery ---------------------------------------------------------------------------------------
+
+def _selection_key_and_table(name: str, mixture: bool, selected_submatrix, selected_submatrix_attention):
+    """Which (module, layer) key and which selection dict a Linear called `name` is looked up in.
+    Mirrors the branch structure of smt.py:98-176."""
+    if "mlp" in name:
+        return (_mlp_kind(name), _layer_of(name)), selected_submatrix
+    if "self_attn" in name:
+        table = selected_submatrix if mixture else selected_submatrix_attention
+        return (_attn_kind(name), _layer_of(name)), table
+    if mixture and "embed_tokens" in name:
+        return ("embed_tokens", None), selected_submatrix
+    return None, None
+
+
+def convert_linear_layer_to_matrix_sparsity(model,
+                                            selected_submatrix,
+                                            selected_submatrix_attention,
+                                            part_module_name=['.layers'],
+                                            mixture=False):
+    """Reference: smt.py:83-179.  Every nn.Linear under `part_module_name` whose weight still requires grad
+    (i.e. survived `freeze_unselected_matrix_layer`) becomes a LinearLayer_MatrixSparsity; bias is dropped
+    (smt.py:113-115); layers without a selected block stay frozen nn.Linear."""
+    names = [name for name, module in model.named_modules()
+             if isinstance(module, nn.Linear) and any(part in name for part in part_module_name)]
+    for name in names:
+        key, table = _selection_key_and_table(name, mixture, selected_submatrix, selected_submatrix_attention)
+        if key is None:
+            continue
+        module = _getattr_path(model, name)
+        if not module.weight.requires_grad:
+            continue
+        _rank0_print(f"Module Test: {name}")
+        index_list = table[key]                            # KeyError here = the reference's behaviour too
+        sparse = LinearLayer_MatrixSparsity(module.weight, bias=None, index_list=index_list)
+        _setattr_path(model, name, sparse.to(module.weight.device).to(module.weight.dtype))
+    return model
+
+
+def convert_matrix_sparsity_to_linear_layer(model, part_module_name=['.layers']):
+    """Reference: smt.py:416-457: write the trained blocks back and restore plain nn.Linear modules that
+    share the (now merged) weight Parameter."""
+    names = [name for name, module in model.named_modules()
+             if isinstance(module, LinearLayer_MatrixSparsity) and any(part in name for part in part_module_name)]
+    for name in names:
+        module = _getattr_path(model, name)
+        module.sync_weight(force=True)
+        out_f, in_f = module.weight.shape
+        linear = nn.Linear(in_f, out_f, bias=False, device="meta")
+        linear = linear.to_empty(device=module.weight.device).to(module.weight.dtype)
+        linear.weight = module.weight                      # smt.py:451 — same Parameter, no clone
+        _setattr_path(model, name, linear)
+    return model
+
+
+def freeze_unselected_matrix_layer(model,
+                                   select_parameters,
+                                   select_attention_parameters,
+                                   mixture=False,
+                                   layernorm=False):
+    """Reference: smt.py:641-745.  requires_grad is True exactly for the parameters of modules that own a
+    selected block (plus layer norms in mixture+layernorm mode); everything else is frozen."""
+    for name, param in model.named_parameters():
+        layer = _layer_of(name)
+        if "mlp" in name:
+            trainable = (_mlp_kind(name), layer) in select_parameters.keys()
+        elif "self_attn" in name:
+            table = select_parameters if mixture else select_attention_parameters
+            trainable = (_attn_kind(name), layer) in table.keys()
+        elif mixture and "embed_tokens" in name:
+            trainable = ("embed_tokens", None) in select_parameters.keys()
+        elif mixture and ("input_layernorm" in name or "post_attention_layernorm" in name):
+            trainable = bool(layernorm)
+        else:
+            trainable = False
+        param.requires_grad = trainable
+    return model
+
+
+def _grouped_parameters(model, weight_decay, base_lr, special_lr, no_decay_name_list, special_name_list):
+    decay, special, no_decay = [], [], []
+    for n, p in model.named_parameters():
+        if not p.requires_grad:
+            continue
+        low = n.lower()
+        if any(nd in low for nd in no_decay_name_list):
+            no_decay.append((n, p))
+        elif any(sp in low for sp in special_name_list):
+            special.append((n, p))
+        else:
+            decay.append((n, p))
+    for tag, items in (("0", decay), ("1", special), ("2", no_decay)):
+        _rank0_print(f"================ PRINT PARAM NAME [{tag}]=======================")
+        for n, _p in items:
+            _rank0_print(f"name{tag}:{n}")
+    groups = [
+        {"params": [p for _n, p in decay], "weight_decay": weight_decay, "lr": base_lr},
+        {"params": [p for _n, p in special], "weight_decay": weight_decay, "lr": special_lr},
+        {"params": [p for _n, p in no_decay], "weight_decay": 0.0},
+    ]
+    return [g for g in groups if g["params"]]
+
+
+def get_optimizer_sparse_grouped_parameters(
+    model,
+    weight_decay,
+    smt_lr,
+    lora_lr=5e-4,
+    no_decay_name_list=["bias", "layer_norm.weight", "layernorm.weight", "norm.weight", "ln_f.weight"],
+    lora_name_list=["lora_right_weight", "lora_left_weight"],
+):
+    """Reference: smt.py:465-549. Group 0 carries lr=smt_lr (it overrides the optimizer's lr); empty groups
+    are dropped, so in practice one group holds every `selected_weight`."""
+    return _grouped_parameters(model, weight_decay, smt_lr, lora_lr, no_decay_name_list, lora_name_list)
+
+
+def get_optimizer_qk_augment_grouped_parameters(
+    model,
+    weight_decay,
+    ft_learning_rate,
+    module_lr=5e-4,
+    no_decay_name_list=["bias", "layer_norm.weight", "layernorm.weight", "norm.weight", "ln_f.weight"],
+    module_name_list=["q_proj", "k_proj"],
+):
+    """Reference: smt.py:554-638 (a full-fine-tuning option of the driver, fine_tune.py:160-163)."""
+    return _grouped_parameters(model, weight_decay, ft_learning_rate, module_lr, no_decay_name_list,
+                               module_name_list)
+
+
+def _channel_path_unsupported(*_args, **_kwargs):
+    raise NotImplementedError(
+        "channel sparsity (smt.py:25-80, 185-296, 748-831) is not part of the B200 hot path: the reference "
+        "implementation selects weight rows but differentiates columns and fails for non-square weights. "
+        "Channel *scoring and selection* are available as smt_helper.select_channel_based_on_activation.")
+
+
+convert_linear_layer_to_channel_sparsity = _channel_path_unsupported
+freeze_unselected_channel_layer = _channel_path_unsupported

@@ -1,0 +1,233 @@
+"""Drop-in mirror of the reference module `deepspeed/smt/smt_helper.py` backed by sm_100a kernels.
+
+Same public names, positional order, defaults and return types as the reference (imported by its driver at
+fine_tune.py:40):
+
+    select_submatrix_based_on_grads   smt_helper.py:40-146    block scores + top-n selection
+    select_channel_based_on_activation smt_helper.py:149-230  channel scores + top-n selection
+    get_blocks                        smt_helper.py:272-294
+    get_named_linears                 smt_helper.py:297-302
+
+Differences from the reference, all deliberate:
+  * scoring and top-k run on the GPU through the C-ABI (`smt_block_score_reduce`, `smt_topk_blocks`); the
+    Python heap with one `.item()` per block is gone.  Selected indices are bit-exact for identical scores,
+    including the tie rule (Python tuple order on (score, ((module, layer), i, j)), larger tuple wins).
+  * importing this module neither initialises a process group nor imports deepspeed / matplotlib
+    (the reference does both at import, smt_helper.py:6-12).
+  * `Block_dimension` is a module global (default 256) instead of a function local (smt_helper.py:52), so
+    the block-size sweep of the benchmarks can patch it; the reference value is unchanged.
+  * `do_gradient_distribution_analysis` (a matplotlib histogram, smt_helper.py:14-38) is out of scope and
+    ignored with a note.
+"""
+from __future__ import annotations
+
+from collections import defaultdict
+from typing import Dict, Hashable, List, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .. import ops
+from .._lib import SMTLibraryError
+
+Block_dimension = 256
+
+_STRATEGIES = ("mean_abs", "abs_mean", "L1", "L2")
+
+
+class UnknownStrategyError(UnboundLocalError, ValueError):
+    """The reference dies with UnboundLocalError at smt_helper.py:142 for an unknown calculate_strategy;
+    this keeps that type while also being a ValueError with a readable message."""
+
+
+class EmptySelectionError(UnboundLocalError, ValueError):
+    """`no_restriction` selection that keeps nothing (n <= 0 or no blocks): the reference crashes with
+    UnboundLocalError at smt_helper.py:141-142 (`del mean` after a loop that never ran); same type here."""
+
+
+def _rank0_print(msg: str) -> None:
+    if not torch.distributed.is_available() or not torch.distributed.is_initialized() \
+            or torch.distributed.get_rank() == 0:
+        print(msg)
+
+
+def _device_for(tensors) -> torch.device:
+    for t in tensors:
+        if isinstance(t, torch.Tensor) and t.is_cuda:
+            return t.device
+    if not torch.cuda.is_available():
+        raise SMTLibraryError("SMT selection runs on the GPU (sm_100a kernels); no CUDA device is available "
+                              "and there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _sorted_keys(keys: Sequence[Hashable]) -> List[Hashable]:
+    try:
+        return sorted(keys)
+    except TypeError:  # e.g. ('embed_tokens', None) next to ('embed_tokens', 3): the reference would raise on a tie
+        return sorted(keys, key=lambda k: tuple((0, "") if p is None else (1, p) for p in (k if isinstance(k, tuple) else (k,))))
+
+
+def _tuple_order_ranks(keys: Sequence[Hashable], sizes: Sequence[int]) -> Tuple[np.ndarray, np.ndarray]:
+    """rank[flat] of entry (key, local index) in Python tuple order, flat layout = concatenation of the
+    matrices in dict order.  Within one key tuple order is (i, j) lexicographic = row-major = local order."""
+    offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    total = int(offsets[-1])
+    rank = np.empty(total, dtype=np.int64)
+    pos = {k: idx for idx, k in enumerate(keys)}
+    base = 0
+    for k in _sorted_keys(keys):
+        idx = pos[k]
+        n = sizes[idx]
+        rank[offsets[idx]:offsets[idx] + n] = base + np.arange(n, dtype=np.int64)
+        base += n
+    inv = np.empty(total, dtype=np.int64)
+    inv[rank] = np.arange(total, dtype=np.int64)
+    return rank.astype(np.int32), inv.astype(np.int32)
+
+
+def _select_from_device_scores(keys, score_tensors, n, selection_strategy, decode):
+    """Shared top-n machinery for blocks and channels.
+    score_tensors: list of contiguous fp32 CUDA tensors (one per key); decode(key_idx, local) -> list item."""
+    ranked = defaultdict(list)
+    if len(keys) == 0:
+        return ranked
+    dev = score_tensors[0].device
+    sizes = [int(t.numel()) for t in score_tensors]
+    flat = torch.cat([t.reshape(-1) for t in score_tensors]) if len(score_tensors) > 1 else score_tensors[0].reshape(-1)
+    flat = flat.contiguous()
+    offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    total = int(offsets[-1])
+    n = int(n)
+    if total == 0 or n <= 0:
+        if selection_strategy != "norm_dist":
+            raise EmptySelectionError(f"nothing to select (n={n}, {total} candidates); the reference raises "
+                                      "UnboundLocalError here (smt_helper.py:141-142)")
+        return ranked
+    if selection_strategy == "norm_dist":
+        # per-matrix top-n (smt_helper.py:81-100). torch.argsort's order among equal scores is unspecified in the
+        # reference; we fix it to "lower flat index first".
+        rank = (total - 1 - np.arange(total, dtype=np.int64)).astype(np.int32)
+        inv = rank.copy()  # the permutation is an involution
+        seg_off = [int(o) for o in offsets]
+        seg_k = [n] * len(keys)
+    else:
+        rank, inv = _tuple_order_ranks(keys, sizes)
+        seg_off = [0, total]
+        seg_k = [n]
+    d_rank = torch.from_numpy(rank).to(dev)
+    d_inv = torch.from_numpy(inv).to(dev)
+    idx, _ = ops.topk_blocks(flat, seg_off, seg_k, d_rank, d_inv)
+    idx_host = idx.cpu().numpy().astype(np.int64)          # the only D2H of the selection: n int32
+    key_idx = np.searchsorted(offsets, idx_host, side="right") - 1
+    local = idx_host - offsets[key_idx]
+    for ki, lo in zip(key_idx.tolist(), local.tolist()):
+        ranked[keys[ki]].append(decode(ki, lo))
+    return ranked
+
+
+def block_scores_on_device(grads: Dict[Hashable, torch.Tensor], targeted_module_dims, calculate_strategy: str,
+                           block: int):
+    """Per-matrix [R/b, C/b] score tensors on the GPU (smt_helper.py:55-78). CPU inputs are copied over
+    one matrix at a time (this is the host-buffer path of the reference's capture loop)."""
+    if calculate_strategy not in _STRATEGIES:
+        raise UnknownStrategyError(f"unknown calculate_strategy {calculate_strategy!r}; expected one of {_STRATEGIES}")
+    dev = _device_for(grads.values())
+    keys, scores, shapes = [], [], []
+    for key, grad in grads.items():
+        name = key[0]
+        d1 = int(targeted_module_dims[name][0] / block)     # smt_helper.py:57-58
+        d2 = int(targeted_module_dims[name][1] / block)
+        g = grad.detach()
+        if not g.is_cuda:
+            g = g.to(dev, non_blocking=False)
+        g = g.to(torch.float32).reshape(d1 * block, d2 * block)   # same element count check as the reference reshape
+        if g.stride(1) != 1:
+            g = g.contiguous()
+        scores.append(ops.block_score_reduce(g, block, calculate_strategy))
+        keys.append(key)
+        shapes.append((d1, d2))
+    return keys, scores, shapes
+
+
+def select_submatrix_from_scores(keys, scores, n, selection_strategy="no_restriction"):
+    """Top-n over already-computed per-matrix score tensors (extension: lets the on-device warm-up
+    accumulator skip the full-size gradient copies). `scores[i]` is a [R/b, C/b] fp32 CUDA tensor."""
+    shapes = [tuple(s.shape) for s in scores]
+    return _select_from_device_scores(list(keys), [s.contiguous() for s in scores], n, selection_strategy,
+                                      lambda ki, lo: (lo // shapes[ki][1], lo % shapes[ki][1]))
+
+
+def select_submatrix_based_on_grads(grads,
+                                    targeted_module_dims,
+                                    n=660,
+                                    selection_strategy="no_restriction",
+                                    calculate_strategy="mean_abs",
+                                    model="yahma/llama-13b-hf",
+                                    do_gradient_distribution_analysis=False,
+                                    output_dir=""):
+    """Reference: smt_helper.py:40-146.
+
+    grads: {(module_name, layer): accumulated fp32 gradient [R, C]} (CPU or CUDA tensors)
+    n: number of blocks to keep — in total for "no_restriction", per matrix for "norm_dist"
+    returns defaultdict(list) {(module_name, layer): [(block_row, block_col), ...]}, best first.
+    """
+    if do_gradient_distribution_analysis:
+        _rank0_print("[smt] gradient-distribution histograms (smt_helper.py:14-38) are not produced by the "
+                     "B200 path; flag ignored")
+    block = Block_dimension
+    keys, scores, _shapes = block_scores_on_device(grads, targeted_module_dims, calculate_strategy, block)
+    return select_submatrix_from_scores(keys, scores, n, selection_strategy)
+
+
+def channel_scores_on_device(activation, calculate_strategy: str):
+    """smt_helper.py:168-183. Accepts the reference's [B, S, C] accumulations or the already batch-reduced
+    [S, C] accumulators of `WarmupActivationAccumulator`."""
+    if calculate_strategy not in _STRATEGIES:
+        raise UnknownStrategyError(f"unknown calculate_strategy {calculate_strategy!r}; expected one of {_STRATEGIES}")
+    dev = _device_for(activation.values())
+    keys, scores = [], []
+    for key, act in activation.items():
+        a = act.detach()
+        if not a.is_cuda:
+            a = a.to(dev)
+        if a.dim() == 3:                                     # smt_helper.py:170: sum_b |act|
+            acc = torch.zeros(a.shape[1:], dtype=torch.float32, device=dev)
+            ops.act_score_accumulate(acc, a.contiguous())
+        else:
+            acc = a.to(torch.float32).contiguous()
+        scores.append(ops.channel_score_reduce(acc, calculate_strategy))
+        keys.append(key)
+    return keys, scores
+
+
+def select_channel_based_on_activation(activation,
+                                       n=660,
+                                       selection_strategy="no_restriction",
+                                       calculate_strategy="mean_abs",
+                                       model="yahma/llama-13b-hf"):
+    """Reference: smt_helper.py:149-230. Returns defaultdict(list) {(module, layer): [channel, ...]}."""
+    keys, scores = channel_scores_on_device(activation, calculate_strategy)
+    return _select_from_device_scores(keys, scores, n, selection_strategy, lambda ki, lo: lo)
+
+
+def get_blocks(model):
+    """Reference: smt_helper.py:272-294 (decoder-layer list lookup by model family)."""
+    cls = model.__class__.__name__
+    low = str(model.__class__).lower()
+    if cls in ("LlamaForCausalLM", "LlavaLlamaForCausalLM"):
+        return model.model.layers
+    if cls == "OPTForCausalLM":
+        return model.model.decoder.layers
+    if cls == "BloomForCausalLM" or "falcon" in low or "bigcode" in low:
+        return model.transformer.h
+    if "mpt" in low:
+        return model.transformer.blocks
+    if "neox" in low:
+        return model.gpt_neox.layers
+    raise NotImplementedError(type(model))
+
+
+def get_named_linears(module):
+    """Reference: smt_helper.py:297-302."""
+    return {name: m for name, m in module.named_modules() if isinstance(m, torch.nn.Linear)}

@@ -1,0 +1,320 @@
+"""GPU parity tests, kernel level: every C-ABI entry point against the CPU oracle on the same seeded inputs.
+Bars: bit-exact for integer / index / byte work (top-k indices, gather, scatter, Adam fp32 state vs the numpy
+restatement); stated tolerances for floating-point reductions and the GEMM."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import smt_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+STRATEGIES = ("mean_abs", "abs_mean", "L1", "L2")
+
+
+@pytest.fixture(scope="module")
+def ops(built_library):
+    from sparse_matrix_tuning_b200 import ops as _ops
+    return _ops
+
+
+# ---- scoring ------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("block", [64, 128, 256])
+@pytest.mark.parametrize("strategy", STRATEGIES)
+def test_block_score_reduce_vs_oracle(ops, block, strategy):
+    torch.manual_seed(block)
+    g = torch.randn(1024, 768)
+    ref = O.block_scores(g, block, strategy)
+    out = ops.block_score_reduce(g.cuda(), block, strategy).cpu()
+    if strategy == "mean_abs":
+        # signed sum: cancellation makes a relative bound meaningless; bound against the block's mean |g| instead
+        scale = O.block_scores(g, block, "abs_mean")
+        assert ((out - ref).abs() <= 2e-6 * scale).all()
+    else:
+        assert torch.allclose(out, ref, rtol=2e-6, atol=0)      # fp32 reduction-order tolerance
+
+
+def test_block_score_reduce_strided_and_exact_cases(ops):
+    base = torch.zeros(512, 1024, device="cuda")
+    view = base[:, 256:768]                                      # ld = 1024, 512 columns
+    view[:256, :256] = 3.0
+    view[256:, 256:] = -2.0
+    for s, want in (("mean_abs", [[3.0, 0.0], [0.0, 2.0]]), ("L1", [[3.0 * 65536, 0.0], [0.0, 2.0 * 65536]]),
+                    ("L2", [[3.0 * 256, 0.0], [0.0, 2.0 * 256]])):
+        assert ops.block_score_reduce(view, 256, s).cpu().tolist() == want
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+def test_score_accumulate_matches_capture_loop(ops, dtype):
+    """fine_tune.py:729-765: acc = sum over steps of grad.float()  (exact: same fp32 adds in the same order)."""
+    torch.manual_seed(1)
+    acc = torch.zeros(256, 520, device="cuda")
+    ref = torch.zeros(256, 520)
+    for _ in range(3):
+        g = torch.randn(256, 520).to(dtype)
+        ops.score_accumulate(acc, g.cuda())
+        ref += g.float()
+    assert torch.equal(acc.cpu(), ref)
+    odd = torch.zeros(1003, device="cuda")
+    g = torch.randn(1003).to(dtype)
+    ops.score_accumulate(odd, g.cuda())
+    assert torch.equal(odd.cpu(), g.float())
+
+
+@pytest.mark.parametrize("block", [64, 256])
+def test_block_sum_mode_reproduces_mean_abs(ops, block):
+    torch.manual_seed(2)
+    sums = torch.zeros(512 // block, 768 // block, device="cuda")
+    total = torch.zeros(512, 768)
+    for _ in range(4):
+        g = torch.randn(512, 768).bfloat16()
+        ops.block_sum_accumulate(sums, g.cuda(), block)
+        total += g.float()
+    ref = O.block_scores(total, block, "mean_abs")
+    scale = O.block_scores(total, block, "abs_mean")
+    got = ops.block_sum_finalize(sums, block).cpu()
+    assert ((got - ref).abs() <= 1e-5 * scale).all()
+
+
+def test_activation_scoring_vs_oracle(ops):
+    torch.manual_seed(3)
+    steps = [torch.randn(3, 40, 512).bfloat16() for _ in range(2)]
+    acc = torch.zeros(40, 512, device="cuda")
+    for x in steps:
+        ops.act_score_accumulate(acc, x.cuda())
+    full = sum(x.float().abs() for x in steps)                   # what the reference hook accumulates, [B, S, C]
+    assert torch.allclose(acc.cpu(), full.sum(0), rtol=1e-6, atol=1e-6)
+    for s in STRATEGIES:
+        ref = O.channel_scores(full, s)
+        assert torch.allclose(ops.channel_score_reduce(acc, s).cpu(), ref, rtol=1e-5, atol=1e-6)
+
+
+# ---- top-k: exact --------------------------------------------------------------------------------------
+
+def _oracle_topk(scores_by_key, n):
+    return O.select_from_scores(scores_by_key, n, "no_restriction")
+
+
+@pytest.mark.parametrize("n_sel", [1, 7, 869, 5000])
+def test_topk_indices_exact_with_ties(ops, n_sel):
+    from sparse_matrix_tuning_b200.smt import smt_helper as H
+    torch.manual_seed(n_sel)
+    keys = [(m, l) for l in (0, 1, 2, 10, 11) for m in ("q_proj", "k_proj", "v_proj")]
+    scores = {}
+    for m, l in keys:
+        shape = (16, 16) if m == "q_proj" else (4, 16)
+        s = torch.randn(shape).abs()
+        s[torch.rand(shape) < 0.4] = 0.5                          # many exact ties across and inside matrices
+        scores[(m, l)] = s
+    n_sel = min(n_sel, sum(s.numel() for s in scores.values()))
+    ref = _oracle_topk(scores, n_sel)
+    got = H.select_submatrix_from_scores(list(scores), [s.cuda() for s in scores.values()], n_sel)
+    assert list(got.items()) == list(ref.items())                 # same keys, same order, same (row, col) order
+
+
+def test_topk_llama8b_size(ops):
+    """12 288 q/k/v block scores, n = 869 (LLaMA-3-8B at 0.71 %) and 98 304 with MLP, n = 2106."""
+    for total, n in ((12288, 869), (98304, 2106)):
+        g = torch.Generator().manual_seed(total)
+        sc = torch.rand(total, generator=g)
+        sc[::5] = 0.25
+        rank = torch.randperm(total, generator=g).int()
+        inv = torch.empty_like(rank)
+        inv[rank.long()] = torch.arange(total, dtype=torch.int32)
+        idx, _ = ops.topk_blocks(sc.cuda(), [0, total], [n], rank.cuda(), inv.cuda())
+        order = sorted(range(total), key=lambda i: (sc[i].item(), rank[i].item()), reverse=True)[:n]
+        assert idx.cpu().tolist() == order
+
+
+def test_topk_segments_and_degenerate_sizes(ops):
+    g = torch.Generator().manual_seed(9)
+    sc = torch.randn(3000, generator=g)
+    offs, ks = [0, 1000, 1000, 2500, 3000], [10, 5, 2000, 7]
+    idx, oo = ops.topk_blocks(sc.cuda(), offs, ks)
+    vals = sc.tolist()
+    for s in range(4):
+        want = [i for _, i in sorted(((vals[i], i) for i in range(offs[s], offs[s + 1])), reverse=True)[:ks[s]]]
+        assert idx[oo[s]:oo[s + 1]].cpu().tolist() == want
+    assert oo == [0, 10, 10, 1510, 1517]
+    big = torch.randn(40000, generator=g)                          # winners exceed shared memory: global-memory sort
+    idx, _ = ops.topk_blocks(big.cuda(), [0, 40000], [20000])
+    want = [i for _, i in sorted(((v, i) for i, v in enumerate(big.tolist())), reverse=True)[:20000]]
+    assert idx.cpu().tolist() == want
+    neg0 = torch.tensor([0.0, -0.0, 0.0, -0.0])                    # -0.0 == +0.0 in the reference's comparison
+    idx, _ = ops.topk_blocks(neg0.cuda(), [0, 4], [4])
+    assert idx.cpu().tolist() == [3, 2, 1, 0]
+
+
+# ---- gather / scatter: byte-exact -------------------------------------------------------------------------
+
+@pytest.mark.parametrize("block", [64, 128, 256])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_gather_scatter_vs_oracle(ops, block, dtype):
+    torch.manual_seed(block)
+    w = torch.randn(512, 768).to(dtype)
+    idx = [(1, 2), (0, 0), (512 // block - 1, 768 // block - 1), (0, 1)]
+    wd = w.cuda()
+    tab = ops.make_block_table([(wd, r, c) for r, c in idx], "cuda")
+    comp = torch.empty(len(idx) * block, block, dtype=dtype, device="cuda")
+    ops.block_gather(tab, len(idx), block, comp)
+    assert torch.equal(comp.cpu(), O.gather_blocks(w, idx, block))
+    new = torch.randn_like(comp)
+    ops.block_scatter(tab, len(idx), block, new)
+    assert torch.equal(wd.cpu(), O.scatter_blocks(w.clone(), new.cpu(), idx, block))
+    ops.block_gather(tab, len(idx), block, comp)                   # round trip
+    assert torch.equal(comp, new)
+
+
+# ---- optimizer ----------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("grad_dtype", [torch.bfloat16, torch.float32])
+def test_compact_adam_bit_exact_vs_numpy_restatement(ops, grad_dtype):
+    """fp32 master / exp_avg / exp_avg_sq after each step are BIT-IDENTICAL to oracle.adamw_fused_step (every op
+    individually rounded), including the in-kernel clip coefficient; bf16 outputs are the RNE rounding of the master."""
+    rng = np.random.RandomState(7)
+    block, n_blocks = 64, 6
+    N = n_blocks * block * block
+    W = torch.randn(256, 256).bfloat16().cuda()
+    idx = [(i // 4, i % 4) for i in range(n_blocks)]
+    tab = ops.make_block_table([(W, r, c) for r, c in idx], "cuda")
+    p = (rng.randn(N) * 0.02).astype(np.float32)
+    m = np.zeros(N, np.float32)
+    v = np.zeros(N, np.float32)
+    dp, dm, dv = (torch.from_numpy(a.copy()).cuda() for a in (p, m, v))
+    comp = torch.empty(N, dtype=torch.bfloat16, device="cuda")
+    hp = dict(lr=3e-4, beta1=0.9, beta2=0.95, eps=1e-8, weight_decay=0.01)
+    for step in range(1, 5):
+        g = torch.from_numpy((rng.randn(N) * (0.05 if step % 2 else 1e-4)).astype(np.float32)).to(grad_dtype)
+        gd = g.cuda()
+        sq = ops.grad_sqnorm(gd)
+        gscale = O.clip_coef(np.float32(sq.item()), np.float32(0.5), np.float32(1.0))
+        ops.compact_adam(dp, dm, dv, gd, step=step, grad_scale=0.5, sqnorm=sq, max_norm=1.0, compact_out=comp,
+                         table=tab, n_blocks=n_blocks, block=block, w_dtype=torch.bfloat16, **hp)
+        p, m, v = O.adamw_fused_step(p, m, v, g.float().numpy(), step=step, gscale=gscale, **hp)
+        assert np.array_equal(dp.cpu().numpy(), p), f"master differs at step {step}"
+        assert np.array_equal(dm.cpu().numpy(), m) and np.array_equal(dv.cpu().numpy(), v)
+        assert np.array_equal(comp.float().cpu().numpy(), O.bf16_round(p))
+        assert torch.equal(O.gather_blocks(W.cpu(), idx, block).reshape(-1), comp.cpu())   # fused write-back
+    # sum of squares vs float64
+    ref_sq = float((g.double() ** 2).sum())
+    assert abs(sq.item() - ref_sq) <= 1e-5 * ref_sq
+
+
+def test_grad_sqnorm_is_deterministic(ops):
+    g = torch.randn(3_000_001, device="cuda").bfloat16()
+    a = ops.grad_sqnorm(g).item()
+    for _ in range(3):
+        assert ops.grad_sqnorm(g).item() == a
+    assert abs(a - float((g.double() ** 2).sum())) <= 1e-5 * a
+
+
+# ---- block-gradient GEMM --------------------------------------------------------------------------------------
+
+def _gemm_inputs(B, S, fin, fout, block, n, dtype, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, S, fin, generator=g).to(dtype)
+    dy = torch.randn(B, S, fout, generator=g).to(dtype)
+    perm = torch.randperm((fout // block) * (fin // block), generator=g)[:n]
+    idx = [(int(p) // (fin // block), int(p) % (fin // block)) for p in perm]
+    return x, dy, idx
+
+
+@pytest.mark.parametrize("block", [64, 128, 256])
+@pytest.mark.parametrize("B,S", [(1, 64), (2, 100), (4, 512)])
+def test_block_grad_gemm_bf16_vs_oracle(ops, block, B, S):
+    """Tolerance: bf16 result within 2^-7 of the tensor max of the fp64 truth AND no worse than the
+    reference's own bf16 arithmetic (per-batch bmm rounded to bf16, then summed in bf16)."""
+    x, dy, idx = _gemm_inputs(B, S, 1024, 768, block, 5, torch.bfloat16, seed=block + S)
+    truth = O.block_grad_truth(x, dy, idx, block)
+    _gi, ref = O.linearz_backward(x, dy, torch.zeros(768, 1024, dtype=torch.bfloat16), idx, block)
+    out = ops.block_grad_gemm(x.cuda().reshape(-1, 1024), dy.cuda().reshape(-1, 768),
+                              ops.make_block_rc(idx, "cuda"), block, out_dtype=torch.bfloat16).cpu()
+    scale = truth.abs().max().item()
+    err = (out.double() - truth).abs().max().item() / scale
+    ref_err = (ref.double() - truth).abs().max().item() / scale
+    assert err <= 2 ** -7
+    # max statistic: 10 % slack (for B == 1 both are one rounding of nearly the same fp32 sum); mean: none
+    assert err <= ref_err * 1.10 + 1e-6, (err, ref_err)
+    assert (out.double() - truth).abs().mean() <= (ref.double() - truth).abs().mean() * 1.001
+    # fp32 output of the same launch: only the fp32 accumulation error remains
+    out32 = ops.block_grad_gemm(x.cuda().reshape(-1, 1024), dy.cuda().reshape(-1, 768),
+                                ops.make_block_rc(idx, "cuda"), block, out_dtype=torch.float32).cpu()
+    assert (out32.double() - truth).abs().max().item() / scale <= 1e-5
+
+
+@pytest.mark.parametrize("block", [64, 128, 256])
+def test_block_grad_gemm_fp32_vs_oracle(ops, block):
+    """fp32 models (BASELINE config 1): 1e-5 of the tensor max, the tolerance north_star's fp32 parity implies."""
+    x, dy, idx = _gemm_inputs(2, 77, 512, 512, block, 4, torch.float32, seed=block)
+    _gi, ref = O.linearz_backward(x, dy, torch.zeros(512, 512), idx, block)
+    out = ops.block_grad_gemm(x.cuda().reshape(-1, 512), dy.cuda().reshape(-1, 512),
+                              ops.make_block_rc(idx, "cuda"), block).cpu()
+    assert (out - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("block", [64, 256])
+def test_block_grad_gemm_split_k_accumulate_and_strides(ops, block):
+    x, dy, idx = _gemm_inputs(1, 4096 + 40, 1024, 512, block, 3, torch.bfloat16, seed=5)
+    truth = O.block_grad_truth(x, dy, idx, block)
+    scale = truth.abs().max().item()
+    xd, dyd = x.cuda().reshape(-1, 1024), dy.cuda().reshape(-1, 512)
+    rc = ops.make_block_rc(idx, "cuda")
+    splits, _ = ops.block_grad_gemm_plan(len(idx), block, xd.shape[0], torch.bfloat16)
+    assert splits > 1                                              # this case exercises the workspace + reduce path
+    base = torch.randn(len(idx) * block, block, device="cuda")
+    out = base.clone()
+    ops.block_grad_gemm(xd, dyd, rc, block, out=out, accumulate=True)
+    assert ((out.cpu().double() - base.cpu().double()) - truth).abs().max().item() / scale <= 2e-5
+    # column-sliced (strided) operands: ld > features
+    xs, dys = xd[:, 256:768], dyd[:, 128:384] if block == 64 else dyd[:, 0:256]
+    idx2 = [(0, 1), ((256 // block) - 1, (512 // block) - 1)]
+    got = ops.block_grad_gemm(xs, dys, ops.make_block_rc(idx2, "cuda"), block, out_dtype=torch.float32).cpu()
+    t2 = O.block_grad_truth(xs.cpu(), dys.cpu(), idx2, block)
+    assert (got.double() - t2).abs().max().item() / t2.abs().max().item() <= 2e-5
+    # run-to-run determinism of the split-K path (fixed-order reduction, no atomics)
+    a = ops.block_grad_gemm(xd, dyd, rc, block, out_dtype=torch.float32)
+    b = ops.block_grad_gemm(xd, dyd, rc, block, out_dtype=torch.float32)
+    assert torch.equal(a, b)
+
+
+def test_block_grad_gemm_empty_inputs(ops):
+    rc = ops.make_block_rc([(0, 0)], "cuda")
+    x = torch.empty(0, 256, device="cuda", dtype=torch.bfloat16)
+    out = ops.block_grad_gemm(x, x, rc, 256, out_dtype=torch.float32)
+    assert out.shape == (256, 256) and not out.any()               # T == 0: the sum over no tokens is zero
+    none = ops.block_grad_gemm(torch.zeros(8, 256, device="cuda", dtype=torch.bfloat16),
+                               torch.zeros(8, 256, device="cuda", dtype=torch.bfloat16),
+                               ops.make_block_rc([], "cuda"), 256)
+    assert none.numel() == 0                                       # no selected block: nothing to do
+
+
+def test_warmup_accumulator_vs_capture_loop(ops):
+    from sparse_matrix_tuning_b200.smt import smt_helper as H
+    from sparse_matrix_tuning_b200.warmup import WarmupGradAccumulator
+    torch.manual_seed(11)
+    names = [f"model.layers.{l}.self_attn.{m}.weight" for l in (0, 1) for m in ("q_proj", "k_proj", "v_proj", "o_proj")]
+    names += ["model.layers.0.mlp.up_proj.weight", "model.embed_tokens.weight"]
+    shapes = {"q_proj": (512, 512), "k_proj": (256, 512), "v_proj": (256, 512), "o_proj": (512, 512),
+              "up_proj": (768, 512), "embed_tokens": (1024, 512)}
+    acc_e = WarmupGradAccumulator(block=256, mode="elementwise")
+    acc_b = WarmupGradAccumulator(block=256, mode="block_sum")
+    ref = {}
+    for _step in range(3):
+        grads = {n: torch.randn(*shapes[[k for k in shapes if k in n][0]]).bfloat16() for n in names}
+
+        class P:  # minimal stand-in for a parameter with .grad
+            def __init__(self, g):
+                self.grad = g
+        params = [(n, P(g.cuda())) for n, g in grads.items()]
+        acc_e.accumulate(params)
+        acc_b.accumulate(params)
+        O.warmup_accumulate(ref, grads.items(), mlp=False, attention=True)
+    assert list(acc_e.grads().keys()) == list(ref.keys())          # o_proj, MLP and embeddings are not captured
+    for k in ref:
+        assert torch.equal(acc_e.grads()[k].cpu(), ref[k])
+    dims = {"q_proj": [512, 512], "k_proj": [256, 512], "v_proj": [256, 512]}
+    want = O.select_submatrix(ref, dims, 6)
+    assert list(H.select_submatrix_based_on_grads(acc_e.grads(), dims, 6).items()) == list(want.items())
+    keys, scores = acc_b.scores("mean_abs")
+    assert list(H.select_submatrix_from_scores(keys, scores, 6).items()) == list(want.items())

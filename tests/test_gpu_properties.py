@@ -1,0 +1,113 @@
+"""GPU tests at BASELINE.json's full sizes, through size-independent properties (the CPU oracle cannot finish
+these sizes in seconds): linearity and token-additivity of the block-gradient contraction, split-K invariance,
+gather->scatter round trips, optimizer idempotence under re-partitioning, top-k sortedness."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops(built_library):
+    from sparse_matrix_tuning_b200 import ops as _ops
+    return _ops
+
+
+def _blocks(fout, fin, b, n, seed):
+    g = torch.Generator().manual_seed(seed)
+    perm = torch.randperm((fout // b) * (fin // b), generator=g)[:n]
+    return [(int(p) // (fin // b), int(p) % (fin // b)) for p in perm]
+
+
+@pytest.mark.parametrize("fin,fout,block,n", [(4096, 4096, 256, 13), (4096, 14336, 256, 45), (14336, 4096, 128, 20),
+                                              (4096, 4096, 64, 100)])
+def test_gemm_full_size_properties(ops, fin, fout, block, n):
+    """Config 2 sizes (4096x4096, 14336x4096, 4096x14336 weights, seq 2048 x batch 4 = 8192 tokens, bf16)."""
+    T = 8192
+    torch.manual_seed(fin + block)
+    x = torch.randn(T, fin, device="cuda").bfloat16()
+    dy1 = torch.randn(T, fout, device="cuda").bfloat16()
+    rc = ops.make_block_rc(_blocks(fout, fin, block, n, seed=n), "cuda")
+    G = ops.block_grad_gemm(x, dy1, rc, block, out_dtype=torch.float32)
+    scale = G.abs().max().item()
+    # (1) spot-check three blocks against torch fp32 matmul (fp32 reference kept for the floating-point kernel)
+    host_rc = rc.cpu().tolist()
+    for i in (0, n // 2, n - 1):
+        r, c = host_rc[i]
+        ref = dy1[:, r * block:(r + 1) * block].float().t() @ x[:, c * block:(c + 1) * block].float()
+        assert (G[i * block:(i + 1) * block] - ref).abs().max().item() <= 2e-5 * scale
+    # (2) additivity over tokens: G(T) == G(first half) + G(second half)  (exercises different split-K plans)
+    h = T // 2 + 64
+    Ga = ops.block_grad_gemm(x[:h], dy1[:h], rc, block, out_dtype=torch.float32)
+    Gb = ops.block_grad_gemm(x[h:], dy1[h:], rc, block, out_dtype=torch.float32)
+    assert (G - (Ga + Gb)).abs().max().item() <= 2e-5 * scale
+    # (3) exact linearity in dy for power-of-two scaling, and sign symmetry
+    G2 = ops.block_grad_gemm(x, dy1 * 2, rc, block, out_dtype=torch.float32)
+    assert torch.equal(G2, G * 2)
+    Gn = ops.block_grad_gemm(x, -dy1, rc, block, out_dtype=torch.float32)
+    assert torch.equal(Gn, -G)
+    # (4) permuting the block list permutes the output rows exactly
+    perm = torch.randperm(n).tolist()
+    rc_p = rc[perm].contiguous()
+    Gp = ops.block_grad_gemm(x, dy1, rc_p, block, out_dtype=torch.float32)
+    assert torch.equal(Gp.view(n, block, block), G.view(n, block, block)[perm])
+    # (5) bf16 output is the RNE rounding of the fp32 output of the same plan
+    Gbf = ops.block_grad_gemm(x, dy1, rc, block, out_dtype=torch.bfloat16)
+    assert torch.equal(Gbf, G.bfloat16())
+
+
+def test_llama8b_compact_state_round_trip_and_adam_repartition(ops):
+    """LLaMA-3-8B at 0.71 %: 869 blocks of 256x256 spread over q/k/v-shaped weights. gather(scatter(c)) == c, and an
+    Adam step over the whole flat state equals the same step run in two halves (elementwise kernel, any partition)."""
+    b, n = 256, 869
+    torch.manual_seed(0)
+    Wq = torch.randn(4096, 4096, device="cuda").bfloat16()
+    Wk = torch.randn(1024, 4096, device="cuda").bfloat16()
+    ents = []
+    for i in range(n):
+        w = Wq if i % 3 else Wk
+        j = i * 7919
+        ents.append((w, j % (w.shape[0] // b), (j // 16) % (w.shape[1] // b)))
+    ents = list({(id(w), r, c): (w, r, c) for w, r, c in ents}.values())   # no duplicate targets
+    n = len(ents)
+    tab = ops.make_block_table(ents, "cuda")
+    comp = torch.randn(n * b, b, device="cuda").bfloat16()
+    ops.block_scatter(tab, n, b, comp)
+    back = torch.empty_like(comp)
+    ops.block_gather(tab, n, b, back)
+    assert torch.equal(back, comp)
+    N = n * b * b
+    g = (torch.randn(N, device="cuda") * 0.01).bfloat16()
+    state = [comp.float().reshape(-1).clone(), torch.zeros(N, device="cuda"), torch.zeros(N, device="cuda")]
+    whole = [t.clone() for t in state]
+    halves = [t.clone() for t in state]
+    sq = ops.grad_sqnorm(g)
+    kw = dict(lr=1e-4, beta1=0.9, beta2=0.95, eps=1e-8, weight_decay=0.0, step=1, sqnorm=sq, max_norm=1.0)
+    ops.compact_adam(*whole, g, table=tab, n_blocks=n, block=b, w_dtype=torch.bfloat16, **kw)
+    h = (n // 2) * b * b
+    ops.compact_adam(*[t[:h] for t in halves], g[:h], **kw)
+    ops.compact_adam(*[t[h:] for t in halves], g[h:], **kw)
+    for a, c in zip(whole, halves):
+        assert torch.equal(a, c)
+    ops.block_gather(tab, n, b, back)                                # fused write-back landed in the dense weights
+    assert torch.equal(back.reshape(-1), whole[0].bfloat16())
+
+
+def test_full_size_scores_and_topk_sorted(ops):
+    """One LLaMA-3-8B q_proj-sized accumulator: block scores of a scaled copy scale exactly (power of two), L1 equals
+    abs_mean * b^2, and the global top-k comes back sorted by (score, index) descending."""
+    torch.manual_seed(1)
+    a = torch.randn(4096, 4096, device="cuda")
+    s1 = ops.block_score_reduce(a, 256, "L1")
+    s2 = ops.block_score_reduce(a * 4, 256, "L1")
+    assert torch.equal(s2, s1 * 4)
+    am = ops.block_score_reduce(a, 256, "abs_mean")
+    assert torch.equal(am, s1 / 65536)
+    ma = ops.block_score_reduce(a, 256, "mean_abs")
+    assert (ma <= am).all()                                           # |mean| <= mean|.|
+    flat = ma.reshape(-1).contiguous()
+    idx, _ = ops.topk_blocks(flat, [0, flat.numel()], [64])
+    vals = flat[idx.long()].cpu().tolist()
+    pairs = list(zip(vals, idx.cpu().tolist()))
+    assert pairs == sorted(pairs, reverse=True) and len(set(idx.cpu().tolist())) == 64
+    assert min(vals) >= torch.kthvalue(flat.cpu(), flat.numel() - 63).values.item()
