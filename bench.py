@@ -239,7 +239,9 @@ def run_ours(args):
     for name, p in named:                                         # capture needs q/k/v weight gradients only
         p.requires_grad = ("self_attn" in name) and any(k in name for k in ("q_proj", "k_proj", "v_proj"))
     if not args.no_ckpt:
-        model.gradient_checkpointing_enable()
+        # non-reentrant checkpointing keeps the whole backward in ONE autograd graph task, so the block-gradient GEMMs
+        # of all modules can be deferred to a single grouped launch at the end of the pass
+        model.gradient_checkpointing_enable(gradient_checkpointing_kwargs={"use_reentrant": False})
         model.enable_input_require_grads()
     model.train()
     torch.cuda.synchronize()
@@ -265,8 +267,7 @@ def run_ours(args):
     opt = SMTAdam(groups, lr=1e-4, betas=(0.9, 0.95), max_grad_norm=1.0)
     n_blocks = sum(len(v) for v in sel.values())
     trainable = opt.trainable_elements()
-    if hasattr(M, "set_grouped_backward"):
-        M.set_grouped_backward(not args.no_group)
+    M.set_grouped_backward(not args.no_group)
     torch.cuda.empty_cache()
 
     def step(ids):
@@ -358,6 +359,7 @@ def run_ours(args):
             "config": {"workload": f"LLaMA-3-8B SMT 0.71% q/k/v gradient-based selection, bf16, seq {S} x batch {B} per GPU"
                                    + ("" if args.layers == 32 else f" [DEBUG: {args.layers} layers only]"),
                        "selected_blocks": n_blocks, "block": BLOCK, "trainable_elements": trainable,
+                       "modules_with_blocks": len(sel), "grouped_block_grad_launch": not args.no_group,
                        "total_blocks_budget_base": total_blocks, "gradient_checkpointing": not args.no_ckpt,
                        "parallelism": f"dp{world}", "tokens_per_step_per_gpu": T,
                        "l2": "inputs larger than L2 (16 GB of weights streamed per step); no explicit flush",

@@ -130,6 +130,25 @@ SMT_API int smt_block_grad_gemm(const void* x, int64_t ldx, int in_features,
                         const int32_t* block_rc, int n_blocks, int block,
                         void* G, int out_dtype, int accumulate,
                         void* workspace, size_t workspace_bytes, void* stream);
+/* Grouped form: the blocks of SEVERAL (x, dy) problems (e.g. every module whose backward ran since the last
+ * flush) in one launch.  `maps` is a device array of 128-byte TMA descriptors produced on the host by
+ * smt_encode_operand_map (one per distinct x or dy operand, all with the same T and dtype); `items` is a device
+ * array with one entry per block: which dy / x descriptor, which block (row, col), and where its b x b result goes
+ * (`out_off` = element offset from `out_base`, a multiple of 8).  Same arithmetic and determinism as the
+ * single-problem call. */
+typedef struct smt_gemm_item {
+  uint32_t map_dy;   /* index into maps: descriptor of the dy operand   */
+  uint32_t map_x;    /* index into maps: descriptor of the x operand    */
+  int32_t  row;      /* block row    (out_features / b index)            */
+  int32_t  col;      /* block column (in_features  / b index)            */
+  int64_t  out_off;  /* element offset of this block's [b, b] output     */
+} smt_gemm_item;
+SMT_API int smt_encode_operand_map(void* map_host, const void* base, int64_t features, int64_t T, int64_t ld,
+                                   int dtype);
+SMT_API size_t smt_block_grad_gemm_grouped_workspace_bytes(int n_items, int block, int64_t T);
+SMT_API int smt_block_grad_gemm_grouped(const void* maps, const smt_gemm_item* items, int n_items, int64_t T,
+                                        int block, int in_dtype, void* out_base, int out_dtype, int accumulate,
+                                        void* workspace, size_t workspace_bytes, void* stream);
 /* introspection for tests/bench: split-K factor and CTA count the launch above would use. */
 SMT_API int smt_block_grad_gemm_plan(int n_blocks, int block, int64_t T, int in_dtype,
                              int* splits_host, int* ctas_host);

@@ -26,6 +26,12 @@ class BlockRef(C.Structure):
     _fields_ = [("w_ptr", C.c_uint64), ("ldw", C.c_int64), ("row", C.c_int32), ("col", C.c_int32)]
 
 
+class GemmItem(C.Structure):
+    """Mirror of `smt_gemm_item`."""
+    _fields_ = [("map_dy", C.c_uint32), ("map_x", C.c_uint32), ("row", C.c_int32), ("col", C.c_int32),
+                ("out_off", C.c_int64)]
+
+
 class SMTLibraryError(RuntimeError):
     pass
 
@@ -48,6 +54,10 @@ _SIGNATURES = {
     "smt_block_grad_gemm_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int64, C.c_int]),
     "smt_block_grad_gemm": (C.c_int, [_P, C.c_int64, C.c_int, _P, C.c_int64, C.c_int, C.c_int64, C.c_int,
                                       _P, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, C.c_size_t, _P]),
+    "smt_encode_operand_map": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int]),
+    "smt_block_grad_gemm_grouped_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int64]),
+    "smt_block_grad_gemm_grouped": (C.c_int, [_P, _P, C.c_int, C.c_int64, C.c_int, C.c_int, _P, C.c_int, C.c_int,
+                                              _P, C.c_size_t, _P]),
     "smt_block_grad_gemm_plan": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_int),
                                            C.POINTER(C.c_int)]),
     "smt_grad_sqnorm_workspace_bytes": (C.c_size_t, []),

@@ -4,8 +4,9 @@
 //
 // The reference issues, per block, a batched cuBLAS bmm ([B,b,S]x[B,S,b]), a reduction over the batch and
 // a slice copy (3 launches per block, results rounded to bf16 per batch entry).  Here ONE grouped launch
-// covers every block of the module: a TMA-fed tcgen05/TMEM GEMM with fp32 accumulation over all T tokens
-// and a single final rounding.
+// covers every block of a module — or, through the grouped entry point, of every module whose backward ran
+// since the last flush: a TMA-fed tcgen05/TMEM GEMM with fp32 accumulation over all T tokens and a single
+// final rounding.
 //
 // Operand layout.  The reduction dimension is the token index t, the SLOW dimension of both row-major
 // inputs, so both UMMA operands are "MN-major": A[m,k] = dy[k, row*b+m] has m contiguous, B[k,n] =
@@ -14,13 +15,17 @@
 // ((8,n),(8,k)):((1,LBO),(8,SBO)) [units of 16 B]: 8 token rows of 128 B form one 1024-B swizzle atom
 // (SBO = 1024 B between 8-token groups) and consecutive 64-feature chunks are LBO = K_TILE*128 B apart.
 //
-// Work decomposition.  Work item = (block, K-split).  One CTA (6 warps: TMA producer, MMA issuer/TMEM
-// owner, 4 epilogue warps) computes the full b x b block for its token range: for b = 256 two M=128
-// accumulators share one x strip (N = 256), using all 512 TMEM columns, which gives the 256x256 tile its
-// 256 flop/B shared-memory-fill intensity.  With few blocks per module (about 9 at 0.71 %) the token range
-// is split across CTAs; partial tiles go to an fp32 workspace and a second kernel sums them in a fixed
-// order (deterministic, no atomics).
+// Work decomposition.  Work item = (tile, K-split); one CTA per item with 10 warps: TMA producer, MMA
+// issuer / TMEM owner, 8 epilogue warps.  For b = 256 a tile is either the whole block (MH = 2: two M=128
+// accumulators share one x strip, N = 256, all 512 TMEM columns, 256 flop per byte of shared-memory fill)
+// or half a block (MH = 1: used when there are few blocks, it halves the split-K partial traffic).  With few
+// tiles per launch the token range is split across CTAs; partial tiles go to an fp32 workspace and a second
+// kernel (launched with programmatic dependent launch, so its launch latency overlaps the GEMM) sums them in
+// a fixed order: deterministic, no atomics.  The epilogue transposes 32x32 accumulator sub-tiles through
+// shared memory so that every global store instruction writes whole 128-byte rows.
 #include <cuda.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -29,22 +34,28 @@ namespace {
 
 constexpr int kKTile = 64;                    // tokens per pipeline stage
 constexpr int kChunkBytes = kKTile * 128;     // one {64 features x K_TILE tokens} TMA box of 16-bit data
-constexpr int kGemmThreads = 192;             // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-5 epilogue
+constexpr int kEpiWarps = 8;
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps;   // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-9 epilogue
 constexpr int kSmemBudget = 200 * 1024;       // pipeline stages (dynamic smem), leaves room for barriers
 constexpr int kMinKTilesPerSplit = 4;
+constexpr int kStageRow = 36;                 // floats per row of the epilogue transpose buffer (32 + 4 pad)
 
-template <int B>
+template <int B, int MH_>
 struct Cfg {
-  static constexpr int MH = B == 256 ? 2 : 1;            // M=128 halves per block
-  static constexpr int A_LOAD = B / 64;                  // A chunks fetched per stage
-  static constexpr int A_SLOTS = A_LOAD < 2 ? 2 : A_LOAD;  // M=128 always spans two chunks
-  static constexpr int B_LOAD = B / 64;                  // N = B
+  static constexpr int MH = MH_;                              // M=128 accumulators per CTA
+  static constexpr int A_LOAD = B >= 128 ? 2 * MH : 1;        // dy chunks fetched per stage
+  static constexpr int A_SLOTS = A_LOAD < 2 ? 2 : A_LOAD;     // an M=128 MMA always spans two chunks
+  static constexpr int B_LOAD = B / 64;                       // N = B
+  static constexpr int TILES_PER_BLOCK = (B == 256 && MH == 1) ? 2 : 1;
+  static constexpr int TILE_ROWS = B >= 128 ? 128 * MH : B;   // output rows one CTA produces
+  static constexpr int TILE_ELEMS = TILE_ROWS * B;
   static constexpr int STAGE_BYTES = (A_SLOTS + B_LOAD) * kChunkBytes;
   static constexpr int STAGES_RAW = kSmemBudget / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int TX_BYTES = (A_LOAD + B_LOAD) * kChunkBytes;
-  static constexpr int TMEM_COLS = MH * B < 32 ? 32 : MH * B;  // 512 / 128 / 64 (powers of two)
+  static constexpr int TMEM_COLS = MH * B < 32 ? 32 : MH * B;  // 512 / 256 / 128 / 64 (powers of two)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + alignment slack
+  static_assert(STAGES * STAGE_BYTES >= kEpiWarps * 32 * kStageRow * 4, "epilogue staging must fit in the pipeline smem");
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------
@@ -96,6 +107,9 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// programmatic dependent launch: let the dependent grid be scheduled / wait for the primary grid's results
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory");
@@ -152,62 +166,74 @@ __host__ __device__ constexpr uint32_t make_idesc(int fmt /*0 = f16, 1 = bf16*/,
 // ---- the tcgen05 kernel ----------------------------------------------------------------------------
 
 struct GemmParams {
-  const int32_t* block_rc;  // [n_blocks][2] (row, col)
-  void* out;                // G (final) when splits == 1, else fp32 workspace
+  const int32_t* block_rc;        // single problem: [n_blocks][2] (row, col)
+  const smt_gemm_item* items;     // grouped: one entry per block
+  const CUtensorMap* maps;        // grouped: tensor maps in global memory (indexed by the items)
+  void* out;                      // G base (single problem: block i at i*b*b; grouped: items[i].out_off)
+  float* ws;                      // fp32 partial tiles when splits > 1
   int splits;
-  int kt_total;             // number of K tiles = ceil(T / kKTile)
+  int kt_total;                   // number of K tiles = ceil(T / kKTile)
   int kt_per_split;
-  int out_dtype;            // of G; the workspace is always fp32
+  int out_dtype;                  // of G; the workspace is always fp32
   int accumulate;
-  int in_fmt;               // 0 = f16, 1 = bf16
+  int in_fmt;                     // 0 = f16, 1 = bf16
 };
 
-template <int B, int ODT, bool ACC>
-__device__ __forceinline__ void store_row_chunk(void* out_base, int64_t elem_off, const uint32_t (&r)[32]) {
-  // 32 consecutive output elements of one row
+template <int ODT, bool ACC>
+__device__ __forceinline__ void store4(void* out_base, int64_t off, float4 v) {
   if (ODT == SMT_F32) {
-    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(out_base) + elem_off);
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
-                             __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
-      if (ACC) {
-        const float4 old = o[q];
-        v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
-      }
-      o[q] = v;
+    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(out_base) + off);
+    if (ACC) {
+      const float4 old = *o;
+      v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
     }
+    *o = v;
   } else {
-    uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(out_base) + elem_off);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      float f[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(r[8 * q + j]);
-      if (ACC) {
-        float old[8];
-        unpack8<ODT>(o[q], old);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] += old[j];
-      }
-      uint4 u;
+    uint2* o = reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(out_base) + off);
+    if (ACC) {
+      const uint2 old = *o;
       if (ODT == SMT_BF16) {
-        u.x = pack_bf16x2(f[0], f[1]); u.y = pack_bf16x2(f[2], f[3]);
-        u.z = pack_bf16x2(f[4], f[5]); u.w = pack_bf16x2(f[6], f[7]);
+        v.x += __uint_as_float(old.x << 16); v.y += __uint_as_float(old.x & 0xffff0000u);
+        v.z += __uint_as_float(old.y << 16); v.w += __uint_as_float(old.y & 0xffff0000u);
       } else {
-        u.x = pack_f16x2(f[0], f[1]); u.y = pack_f16x2(f[2], f[3]);
-        u.z = pack_f16x2(f[4], f[5]); u.w = pack_f16x2(f[6], f[7]);
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&old.x));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&old.y));
+        v.x += a.x; v.y += a.y; v.z += b.x; v.w += b.y;
       }
-      o[q] = u;
     }
+    uint2 u;
+    if (ODT == SMT_BF16) { u.x = pack_bf16x2(v.x, v.y); u.y = pack_bf16x2(v.z, v.w); }
+    else { u.x = pack_f16x2(v.x, v.y); u.y = pack_f16x2(v.z, v.w); }
+    *o = u;
   }
 }
 
-template <int B>
+// One 32x32 fp32 accumulator sub-tile (lane = row, r[] = 32 columns) -> global, transposed through a per-warp
+// shared-memory buffer so that each store instruction covers 4 rows x 128 B (fp32) / 64 B (16-bit).
+template <int ODT, bool ACC>
+__device__ __forceinline__ void store_subtile(float* stage, const uint32_t (&r)[32], int lane, void* out_base,
+                                              int64_t off00, int ld) {
+  float4* mine = reinterpret_cast<float4*>(stage + lane * kStageRow);
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    mine[q] = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                          __uint_as_float(r[4 * q + 3]));
+  __syncwarp();
+  const int sub = lane >> 3, cv = (lane & 7) * 4;
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int row = it * 4 + sub;
+    const float4 v = *reinterpret_cast<const float4*>(stage + row * kStageRow + cv);
+    store4<ODT, ACC>(out_base, off00 + (int64_t)row * ld + cv, v);
+  }
+  __syncwarp();
+}
+
+template <int B, int MH, bool GROUPED>
 __global__ void __launch_bounds__(kGemmThreads, 1) block_grad_umma_kernel(
     const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
     const GemmParams p) {
-  using C = Cfg<B>;
+  using C = Cfg<B, MH>;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[C::STAGES];
   __shared__ __align__(8) uint64_t empty_bar[C::STAGES];
@@ -215,19 +241,36 @@ __global__ void __launch_bounds__(kGemmThreads, 1) block_grad_umma_kernel(
   __shared__ uint32_t tmem_slot;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int blk = blockIdx.x, split = blockIdx.y;
+  const int tile = blockIdx.x, split = blockIdx.y;
+  const int blk = tile / C::TILES_PER_BLOCK, half = tile % C::TILES_PER_BLOCK;
   const int kt_begin = split * p.kt_per_split;
   const int kt_end = min(kt_begin + p.kt_per_split, p.kt_total);
   const int n_kt = kt_end - kt_begin;  // >= 1 by construction of the plan
 
   // 1024-byte aligned pipeline buffers (SWIZZLE_128B atoms are 1024 B)
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   auto a_addr = [&](int stage) { return smem_base + stage * C::STAGE_BYTES; };
   auto b_addr = [&](int stage) { return smem_base + stage * C::STAGE_BYTES + C::A_SLOTS * kChunkBytes; };
 
+  int row, col;
+  const CUtensorMap* map_x = &tmap_x;
+  const CUtensorMap* map_dy = &tmap_dy;
+  int64_t out_off;                       // element offset of this tile's first output row
+  if (GROUPED) {
+    const smt_gemm_item item = p.items[blk];
+    row = item.row; col = item.col;
+    map_x = p.maps + item.map_x;
+    map_dy = p.maps + item.map_dy;
+    out_off = item.out_off + (int64_t)half * 128 * B;
+  } else {
+    row = p.block_rc[2 * blk]; col = p.block_rc[2 * blk + 1];
+    out_off = (int64_t)tile * C::TILE_ELEMS;
+  }
+
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tmap_x);
-    prefetch_tmap(&tmap_dy);
+    prefetch_tmap(map_x);
+    prefetch_tmap(map_dy);
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
       mbar_init(smem_u32(&empty_bar[s]), 1);
@@ -240,11 +283,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) block_grad_umma_kernel(
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
+  if (threadIdx.x == 0) pdl_launch_dependents();   // the split-K reduce grid may get scheduled (it waits for us)
 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      const int row = p.block_rc[2 * blk], col = p.block_rc[2 * blk + 1];
+      const int a_col0 = row * B + half * 128;
       for (int it = 0; it < n_kt; ++it) {
         const int stage = it % C::STAGES;
         const uint32_t phase = (uint32_t)(it / C::STAGES) & 1u;
@@ -254,10 +298,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) block_grad_umma_kernel(
         const int t0 = (kt_begin + it) * kKTile;
 #pragma unroll
         for (int c = 0; c < C::A_LOAD; ++c)
-          tma_load_2d(a_addr(stage) + c * kChunkBytes, &tmap_dy, fb, row * B + c * 64, t0);
+          tma_load_2d(a_addr(stage) + c * kChunkBytes, map_dy, fb, a_col0 + c * 64, t0);
 #pragma unroll
         for (int c = 0; c < C::B_LOAD; ++c)
-          tma_load_2d(b_addr(stage) + c * kChunkBytes, &tmap_x, fb, col * B + c * 64, t0);
+          tma_load_2d(b_addr(stage) + c * kChunkBytes, map_x, fb, col * B + c * 64, t0);
       }
     }
   } else if (warp == 1) {
@@ -274,7 +318,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) block_grad_umma_kernel(
           // 16 tokens = two 8-row swizzle atoms = 2048 B further down every chunk
           const uint64_t bdesc = make_desc_mn_sw128(b_addr(stage) + k * 2048, kChunkBytes, 1024);
 #pragma unroll
-          for (int mh = 0; mh < C::MH; ++mh) {
+          for (int mh = 0; mh < MH; ++mh) {
             const uint64_t adesc =
                 make_desc_mn_sw128(a_addr(stage) + mh * 2 * kChunkBytes + k * 2048, kChunkBytes, 1024);
             umma_f16(tmem_base + mh * B, adesc, bdesc, idesc, (it > 0 || k > 0) ? 1u : 0u);
@@ -285,36 +329,39 @@ __global__ void __launch_bounds__(kGemmThreads, 1) block_grad_umma_kernel(
       umma_commit(smem_u32(&tmem_full_bar));       // accumulators complete
     }
   } else {
-    // ===== epilogue: TMEM -> registers -> global =====
+    // ===== epilogue: TMEM -> registers -> smem transpose -> coalesced global stores =====
+    const int ew = warp - 2;            // 0..7
     const int q = warp & 3;             // TMEM lane quarter this warp may access
-    const int m = q * 32 + lane;        // accumulator row (0..127)
+    const int par = ew >> 2;            // two warps per quarter: even / odd column chunks
+    constexpr int ROWS_PER_MH = B < 128 ? B : 128;
     mbar_wait(smem_u32(&tmem_full_bar), 0);
     tc_fence_after();
-    const bool final_out = (p.splits == 1);
-    const int64_t tile_elems = (int64_t)B * B;
-    constexpr int ROWS_VALID = B < 128 ? B : 128;
+    if (q * 32 < ROWS_PER_MH) {
+      // all MMAs have retired => the pipeline buffers are dead; reuse them as transpose staging
+      float* stage = reinterpret_cast<float*>(smem_gen) + ew * 32 * kStageRow;
+      const bool final_out = (p.splits == 1);
+      float* part = p.ws + ((int64_t)tile * p.splits + split) * C::TILE_ELEMS;
 #pragma unroll 1
-    for (int mh = 0; mh < C::MH; ++mh) {
+      for (int mh = 0; mh < MH; ++mh) {
 #pragma unroll 1
-      for (int cc = 0; cc < B / 32; ++cc) {
-        uint32_t r[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mh * B + cc * 32), r);
-        tmem_ld_wait();
-        if (m < ROWS_VALID) {
-          const int64_t off_in_tile = (int64_t)(mh * 128 + m) * B + cc * 32;
+        for (int cc = par; cc < B / 32; cc += 2) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mh * B + cc * 32), r);
+          tmem_ld_wait();
+          const int64_t off_in_tile = (int64_t)(mh * 128 + q * 32) * B + cc * 32;
           if (!final_out) {
-            store_row_chunk<B, SMT_F32, false>(p.out, ((int64_t)blk * p.splits + split) * tile_elems + off_in_tile, r);
+            store_subtile<SMT_F32, false>(stage, r, lane, part, off_in_tile, B);
           } else {
-            const int64_t off = (int64_t)blk * tile_elems + off_in_tile;
+            const int64_t off = out_off + off_in_tile;
             if (p.out_dtype == SMT_F32) {
-              if (p.accumulate) store_row_chunk<B, SMT_F32, true>(p.out, off, r);
-              else store_row_chunk<B, SMT_F32, false>(p.out, off, r);
+              if (p.accumulate) store_subtile<SMT_F32, true>(stage, r, lane, p.out, off, B);
+              else store_subtile<SMT_F32, false>(stage, r, lane, p.out, off, B);
             } else if (p.out_dtype == SMT_BF16) {
-              if (p.accumulate) store_row_chunk<B, SMT_BF16, true>(p.out, off, r);
-              else store_row_chunk<B, SMT_BF16, false>(p.out, off, r);
+              if (p.accumulate) store_subtile<SMT_BF16, true>(stage, r, lane, p.out, off, B);
+              else store_subtile<SMT_BF16, false>(stage, r, lane, p.out, off, B);
             } else {
-              if (p.accumulate) store_row_chunk<B, SMT_F16, true>(p.out, off, r);
-              else store_row_chunk<B, SMT_F16, false>(p.out, off, r);
+              if (p.accumulate) store_subtile<SMT_F16, true>(stage, r, lane, p.out, off, B);
+              else store_subtile<SMT_F16, false>(stage, r, lane, p.out, off, B);
             }
           }
         }
@@ -334,13 +381,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1) block_grad_umma_kernel(
 
 template <int ODT>
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, void* __restrict__ out,
-                                                            int64_t tile_elems, int splits, int64_t n_vec8,
-                                                            int accumulate) {
+                                                            const smt_gemm_item* __restrict__ items,
+                                                            int tile_elems, int tiles_per_block, int half_elems,
+                                                            int splits, int64_t n_vec8, int accumulate) {
+  pdl_wait();  // programmatic dependent launch: the GEMM grid's partial tiles are complete and visible
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t vec = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; vec < n_vec8; vec += stride) {
     const int64_t e = vec * 8;
-    const int64_t blk = e / tile_elems, within = e - blk * tile_elems;
-    const float* src = ws + blk * splits * tile_elems + within;
+    const int64_t tile = e / tile_elems;
+    const int within = (int)(e - tile * tile_elems);
+    const float* src = ws + tile * splits * tile_elems + within;
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int s = 0; s < splits; ++s) {
       const float4 a = ld_stream_f4(src + (int64_t)s * tile_elems);
@@ -348,21 +398,24 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
       acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
       acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
     }
+    int64_t o = e;
+    if (items != nullptr)
+      o = items[tile / tiles_per_block].out_off + (int64_t)(tile % tiles_per_block) * half_elems + within;
     if (ODT == SMT_F32) {
-      float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + e);
+      float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + o);
       float4 v0 = make_float4(acc[0], acc[1], acc[2], acc[3]), v1 = make_float4(acc[4], acc[5], acc[6], acc[7]);
       if (accumulate) {
-        const float4 o0 = o[0], o1 = o[1];
+        const float4 o0 = op[0], o1 = op[1];
         v0.x += o0.x; v0.y += o0.y; v0.z += o0.z; v0.w += o0.w;
         v1.x += o1.x; v1.y += o1.y; v1.z += o1.z; v1.w += o1.w;
       }
-      o[0] = v0;
-      o[1] = v1;
+      op[0] = v0;
+      op[1] = v1;
     } else {
-      uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(out) + e);
+      uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(out) + o);
       if (accumulate) {
         float old[8];
-        unpack8<ODT>(*o, old);
+        unpack8<ODT>(*op, old);
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] += old[j];
       }
@@ -374,7 +427,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
         u.x = pack_f16x2(acc[0], acc[1]); u.y = pack_f16x2(acc[2], acc[3]);
         u.z = pack_f16x2(acc[4], acc[5]); u.w = pack_f16x2(acc[6], acc[7]);
       }
-      *o = u;
+      *op = u;
     }
   }
 }
@@ -438,19 +491,60 @@ __global__ void __launch_bounds__(256) block_grad_f32_kernel(const float* __rest
 // ---- host side ------------------------------------------------------------------------------------------
 
 struct Plan {
-  int splits, kt_total, kt_per_split;
+  int mh;             // M=128 accumulators per CTA (2 = whole 256-block per CTA)
+  int tiles;          // CTAs along x
+  int splits;         // CTAs along y (K splits)
+  int kt_total, kt_per_split;
+  int tile_elems;
 };
 
-Plan make_plan(int n_blocks, int64_t T) {
-  Plan pl;
-  pl.kt_total = (int)((T + kKTile - 1) / kKTile);
-  int splits = sm_count() / (n_blocks > 0 ? n_blocks : 1);
-  int max_by_work = pl.kt_total / kMinKTilesPerSplit;
-  if (splits > max_by_work) splits = max_by_work;
-  if (splits < 1) splits = 1;
-  pl.kt_per_split = (pl.kt_total + splits - 1) / splits;
-  pl.splits = (pl.kt_total + pl.kt_per_split - 1) / pl.kt_per_split;  // drop empty tails
-  return pl;
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
+// Picks the tile shape and the split-K factor by minimising a small cost model (microseconds):
+//
+//     cost = 4 + waves * (5 + kt * c_kt + epilogue) + [splits > 1] * (8 + partial_bytes / 4 MB/us)
+//
+// fitted on B200 over tools/sweep_plan.py (profiles/r01_plan_sweep_raw.txt; typical error < 8 %).  c_kt is the
+// measured time per 64-token K tile: 0.64 us for a whole 256-block per CTA (two M=128 UMMAs per K step, 84 % of the
+// UMMA issue rate), 0.41 us for a half block, 0.30 us for b = 128 / 64 (latency-bound pipeline).  Splitting K costs a
+// second (reduce) kernel plus writing and re-reading the fp32 partial tiles, so small launches prefer half-block
+// tiles (half the partial bytes for the same CTA count) and one wave of CTAs.
+Plan make_plan(int n_blocks, int block, int64_t T) {
+  const int sms = sm_count();
+  Plan best{};
+  const int kt_total = (int)((T + kKTile - 1) / kKTile);
+  double best_cost = 1e30;
+  const int force_mh = env_int("SMT_GEMM_FORCE_MH", 0), force_splits = env_int("SMT_GEMM_FORCE_SPLITS", 0);
+  for (int mh = 1; mh <= (block == 256 ? 2 : 1); ++mh) {
+    if (force_mh && mh != force_mh && block == 256) continue;
+    const int tpb = (block == 256 && mh == 1) ? 2 : 1;
+    const int tiles = n_blocks * tpb;
+    const int tile_rows = block >= 128 ? 128 * mh : block;
+    const double tile_bytes = 4.0 * tile_rows * block;                 // fp32 tile
+    const double c_kt = block == 256 ? (mh == 2 ? 0.64 : 0.41) : 0.30;
+    int max_splits = kt_total / kMinKTilesPerSplit;
+    if (max_splits < 1) max_splits = 1;
+    if (max_splits > 64) max_splits = 64;
+    for (int s = 1; s <= max_splits; ++s) {
+      if (force_splits && s != (force_splits > max_splits ? max_splits : force_splits)) continue;
+      const int kt = (kt_total + s - 1) / s;
+      const int s_eff = (kt_total + kt - 1) / kt;
+      const long ctas = (long)tiles * s_eff;
+      const long waves = (ctas + sms - 1) / sms;
+      const double epi = tile_bytes / 131072.0 * (s_eff > 1 ? 2.0 : 1.0);
+      double cost = 4.0 + waves * (5.0 + kt * c_kt + epi);
+      if (s_eff > 1) cost += 8.0 + (double)ctas * tile_bytes / 4.0e6;
+      if (cost < best_cost) {
+        best_cost = cost;
+        best.mh = mh; best.tiles = tiles; best.splits = s_eff; best.kt_total = kt_total; best.kt_per_split = kt;
+        best.tile_elems = tile_rows * block;
+      }
+    }
+  }
+  return best;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -491,17 +585,61 @@ int encode_operand_map(CUtensorMap* map, const void* base, int64_t features, int
   return SMT_OK;
 }
 
-template <int B>
-int launch_umma(const CUtensorMap& mx, const CUtensorMap& mdy, const GemmParams& gp, int n_blocks, cudaStream_t st) {
-  using C = Cfg<B>;
-  SMT_CHECK_CUDA(cudaFuncSetAttribute(block_grad_umma_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-  dim3 grid(n_blocks, gp.splits);
-  block_grad_umma_kernel<B><<<grid, kGemmThreads, C::SMEM_BYTES, st>>>(mx, mdy, gp);
+template <int B, int MH, bool GROUPED>
+int launch_umma_cfg(const CUtensorMap& mx, const CUtensorMap& mdy, const GemmParams& gp, const Plan& pl, cudaStream_t st) {
+  using C = Cfg<B, MH>;
+  auto kern = block_grad_umma_kernel<B, MH, GROUPED>;
+  SMT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  dim3 grid(pl.tiles, pl.splits);
+  kern<<<grid, kGemmThreads, C::SMEM_BYTES, st>>>(mx, mdy, gp);
   SMT_CHECK_LAUNCH();
   return SMT_OK;
 }
 
+template <bool GROUPED>
+int launch_umma(int block, const CUtensorMap& mx, const CUtensorMap& mdy, const GemmParams& gp, const Plan& pl,
+                cudaStream_t st) {
+  if (block == 256) {
+    if (pl.mh == 2) return launch_umma_cfg<256, 2, GROUPED>(mx, mdy, gp, pl, st);
+    return launch_umma_cfg<256, 1, GROUPED>(mx, mdy, gp, pl, st);
+  }
+  if (block == 128) return launch_umma_cfg<128, 1, GROUPED>(mx, mdy, gp, pl, st);
+  return launch_umma_cfg<64, 1, GROUPED>(mx, mdy, gp, pl, st);
+}
+
+// split-K reduce, launched with programmatic stream serialization so that its launch overlaps the GEMM
+int launch_reduce(const float* ws, void* out, const smt_gemm_item* items, int block, const Plan& pl, int n_blocks,
+                  int out_dtype, int accumulate, cudaStream_t st) {
+  const int64_t n_out = (int64_t)n_blocks * block * block;
+  const int64_t n_vec8 = n_out / 8;
+  int64_t want = (n_vec8 + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(want < cap ? want : cap));
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const int tpb = pl.tiles / n_blocks;
+  const int half_elems = 128 * block;
+  if (out_dtype == SMT_F32)
+    SMT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, splitk_reduce_kernel<SMT_F32>, ws, out, items, pl.tile_elems, tpb, half_elems, pl.splits, n_vec8, accumulate));
+  else if (out_dtype == SMT_BF16)
+    SMT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, splitk_reduce_kernel<SMT_BF16>, ws, out, items, pl.tile_elems, tpb, half_elems, pl.splits, n_vec8, accumulate));
+  else
+    SMT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, splitk_reduce_kernel<SMT_F16>, ws, out, items, pl.tile_elems, tpb, half_elems, pl.splits, n_vec8, accumulate));
+  return SMT_OK;
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+size_t plan_workspace_bytes(const Plan& pl) {
+  return pl.splits > 1 ? (size_t)pl.tiles * pl.splits * pl.tile_elems * sizeof(float) : 0;
+}
 
 }  // namespace
 }  // namespace smt
@@ -517,9 +655,9 @@ extern "C" SMT_API int smt_block_grad_gemm_plan(int n_blocks, int block, int64_t
     if (in_dtype == SMT_F32) {
       ctas = n_blocks * (block / 64) * (block / 64);
     } else {
-      Plan pl = make_plan(n_blocks, T);
+      Plan pl = make_plan(n_blocks, block, T);
       splits = pl.splits;
-      ctas = n_blocks * pl.splits;
+      ctas = pl.tiles * pl.splits;
     }
   }
   if (splits_host) *splits_host = splits;
@@ -529,9 +667,7 @@ extern "C" SMT_API int smt_block_grad_gemm_plan(int n_blocks, int block, int64_t
 
 extern "C" SMT_API size_t smt_block_grad_gemm_workspace_bytes(int n_blocks, int block, int64_t T, int in_dtype) {
   if (n_blocks <= 0 || T <= 0 || !block_ok(block) || in_dtype == SMT_F32) return 0;
-  Plan pl = make_plan(n_blocks, T);
-  if (pl.splits <= 1) return 0;
-  return (size_t)n_blocks * pl.splits * block * block * sizeof(float);
+  return plan_workspace_bytes(make_plan(n_blocks, block, T));
 }
 
 extern "C" SMT_API int smt_block_grad_gemm(const void* x, int64_t ldx, int in_features, const void* dy, int64_t lddy,
@@ -572,9 +708,8 @@ extern "C" SMT_API int smt_block_grad_gemm(const void* x, int64_t ldx, int in_fe
   }
 
   SMT_CHECK_ARG(T < (1ll << 31) - kKTile, "smt_block_grad_gemm: T too large");
-  Plan pl = make_plan(n_blocks, T);
-  SMT_CHECK_ARG(pl.splits <= 65535, "smt_block_grad_gemm: too many splits");
-  const size_t need = smt_block_grad_gemm_workspace_bytes(n_blocks, block, T, in_dtype);
+  const Plan pl = make_plan(n_blocks, block, T);
+  const size_t need = plan_workspace_bytes(pl);
   if (need > 0 && (workspace == nullptr || workspace_bytes < need)) {
     set_error("smt_block_grad_gemm: workspace too small (%zu < %zu)", workspace_bytes, need);
     return SMT_ERR_WORKSPACE;
@@ -585,33 +720,73 @@ extern "C" SMT_API int smt_block_grad_gemm(const void* x, int64_t ldx, int in_fe
   if (int rc = encode_operand_map(&mx, x, in_features, T, ldx, in_dtype)) return rc;
   if (int rc = encode_operand_map(&mdy, dy, out_features, T, lddy, in_dtype)) return rc;
 
-  GemmParams gp;
+  GemmParams gp{};
   gp.block_rc = block_rc;
-  gp.out = pl.splits == 1 ? G : workspace;
+  gp.out = G;
+  gp.ws = reinterpret_cast<float*>(workspace);
   gp.splits = pl.splits;
   gp.kt_total = pl.kt_total;
   gp.kt_per_split = pl.kt_per_split;
   gp.out_dtype = out_dtype;
   gp.accumulate = accumulate;
   gp.in_fmt = in_dtype == SMT_BF16 ? 1 : 0;
+  if (int rc = launch_umma<false>(block, mx, mdy, gp, pl, st)) return rc;
+  if (pl.splits > 1) return launch_reduce(gp.ws, G, nullptr, block, pl, n_blocks, out_dtype, accumulate, st);
+  return SMT_OK;
+}
 
-  int rc;
-  if (block == 256) rc = launch_umma<256>(mx, mdy, gp, n_blocks, st);
-  else if (block == 128) rc = launch_umma<128>(mx, mdy, gp, n_blocks, st);
-  else rc = launch_umma<64>(mx, mdy, gp, n_blocks, st);
-  if (rc) return rc;
+// ---- grouped entry point: blocks of several (x, dy) problems in one launch ----------------------------------
 
-  if (pl.splits > 1) {
-    const int64_t n_vec8 = n_out / 8;
-    int64_t want = (n_vec8 + 255) / 256;
-    const int64_t cap = (int64_t)sm_count() * 8;
-    const int grid = (int)(want < cap ? want : cap);
-    const float* ws = reinterpret_cast<const float*>(workspace);
-    const int64_t tile = (int64_t)block * block;
-    if (out_dtype == SMT_F32) splitk_reduce_kernel<SMT_F32><<<grid, 256, 0, st>>>(ws, G, tile, pl.splits, n_vec8, accumulate);
-    else if (out_dtype == SMT_BF16) splitk_reduce_kernel<SMT_BF16><<<grid, 256, 0, st>>>(ws, G, tile, pl.splits, n_vec8, accumulate);
-    else splitk_reduce_kernel<SMT_F16><<<grid, 256, 0, st>>>(ws, G, tile, pl.splits, n_vec8, accumulate);
-    SMT_CHECK_LAUNCH();
+extern "C" SMT_API int smt_encode_operand_map(void* map_host, const void* base, int64_t features, int64_t T,
+                                              int64_t ld, int dtype) {
+  SMT_CHECK_ARG(map_host && base, "smt_encode_operand_map: null pointer");
+  SMT_CHECK_ARG(dtype == SMT_BF16 || dtype == SMT_F16, "smt_encode_operand_map: 16-bit operands only");
+  SMT_CHECK_ARG((reinterpret_cast<uintptr_t>(map_host) & 63u) == 0, "smt_encode_operand_map: map must be 64-byte aligned");
+  SMT_CHECK_ARG(features > 0 && T > 0 && ld >= features && (ld * 2) % 16 == 0 && aligned16(base),
+                "smt_encode_operand_map: bad operand geometry");
+  static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap is 128 bytes");
+  return encode_operand_map(reinterpret_cast<CUtensorMap*>(map_host), base, features, T, ld, dtype);
+}
+
+extern "C" SMT_API size_t smt_block_grad_gemm_grouped_workspace_bytes(int n_items, int block, int64_t T) {
+  if (n_items <= 0 || T <= 0 || !block_ok(block)) return 0;
+  return plan_workspace_bytes(make_plan(n_items, block, T));
+}
+
+extern "C" SMT_API int smt_block_grad_gemm_grouped(const void* maps, const smt_gemm_item* items, int n_items,
+                                                   int64_t T, int block, int in_dtype, void* out_base, int out_dtype,
+                                                   int accumulate, void* workspace, size_t workspace_bytes,
+                                                   void* stream) {
+  SMT_CHECK_ARG(n_items >= 0 && T >= 0, "smt_block_grad_gemm_grouped: negative size");
+  if (n_items == 0 || T == 0) return SMT_OK;
+  SMT_CHECK_ARG(block_ok(block), "smt_block_grad_gemm_grouped: block size %d not in {64,128,256}", block);
+  SMT_CHECK_ARG(maps && items && out_base, "smt_block_grad_gemm_grouped: null pointer");
+  SMT_CHECK_ARG((in_dtype == SMT_BF16 || in_dtype == SMT_F16) && out_dtype >= SMT_F32 && out_dtype <= SMT_F16,
+                "smt_block_grad_gemm_grouped: bad dtype");
+  SMT_CHECK_ARG((reinterpret_cast<uintptr_t>(maps) & 63u) == 0 && aligned16(out_base),
+                "smt_block_grad_gemm_grouped: maps must be 64-byte and out_base 16-byte aligned");
+  SMT_CHECK_ARG(T < (1ll << 31) - kKTile, "smt_block_grad_gemm_grouped: T too large");
+  const Plan pl = make_plan(n_items, block, T);
+  const size_t need = plan_workspace_bytes(pl);
+  if (need > 0 && (workspace == nullptr || workspace_bytes < need)) {
+    set_error("smt_block_grad_gemm_grouped: workspace too small (%zu < %zu)", workspace_bytes, need);
+    return SMT_ERR_WORKSPACE;
   }
+  cudaStream_t st = (cudaStream_t)stream;
+  GemmParams gp{};
+  gp.items = items;
+  gp.maps = reinterpret_cast<const CUtensorMap*>(maps);
+  gp.out = out_base;
+  gp.ws = reinterpret_cast<float*>(workspace);
+  gp.splits = pl.splits;
+  gp.kt_total = pl.kt_total;
+  gp.kt_per_split = pl.kt_per_split;
+  gp.out_dtype = out_dtype;
+  gp.accumulate = accumulate;
+  gp.in_fmt = in_dtype == SMT_BF16 ? 1 : 0;
+  CUtensorMap dummy;
+  memset(&dummy, 0, sizeof(dummy));
+  if (int rc = launch_umma<true>(block, dummy, dummy, gp, pl, st)) return rc;
+  if (pl.splits > 1) return launch_reduce(gp.ws, out_base, items, block, pl, n_items, out_dtype, accumulate, st);
   return SMT_OK;
 }

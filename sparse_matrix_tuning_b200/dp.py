@@ -46,6 +46,8 @@ def allreduce_sum_(tensors: Iterable[torch.Tensor], group=None, async_op: bool =
 
 def allreduce_compact_grads(optimizer, group=None, async_op: bool = False):
     """SUM-all-reduce the optimizer's flat gradient buffers and fold the 1/world mean into its `grad_scale`."""
+    from .smt.smt import flush_block_grads
+    flush_block_grads()                                      # the flat buffer must be complete before it is reduced
     ws = world_size(group)
     optimizer.grad_scale = 1.0 / ws
     return allreduce_sum_(optimizer.flat_grads(), group=group, async_op=async_op)

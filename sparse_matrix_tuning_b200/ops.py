@@ -310,3 +310,82 @@ def compact_adam(master: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.
 
 
 BF16_ID = _lib.BF16
+
+
+# ---- grouped block-gradient GEMM: several (x, dy) problems in one launch ------------------------------------
+
+class BlockGradBatch:
+    """Collects block-gradient problems (one per module backward) and runs them as ONE grouped tcgen05 launch.
+
+    add() keeps references to the operands; flush() encodes one TMA descriptor per distinct operand on the host,
+    ships descriptors + per-block work items with a single pinned H2D copy and launches
+    `smt_block_grad_gemm_grouped`.  Problems must share T, the input dtype, the output dtype and the block size
+    (flush() launches one group per distinct combination)."""
+
+    def __init__(self):
+        self.problems = []
+
+    def __len__(self):
+        return len(self.problems)
+
+    def add(self, x2d: torch.Tensor, dy2d: torch.Tensor, index_list, out: torch.Tensor, block: int) -> None:
+        require_cuda(x2d, dy2d, out)
+        assert x2d.dim() == 2 and dy2d.dim() == 2 and x2d.shape[0] == dy2d.shape[0] and x2d.dtype == dy2d.dtype
+        assert x2d.stride(1) == 1 and dy2d.stride(1) == 1 and out.is_contiguous()
+        assert out.numel() == len(index_list) * block * block
+        self.problems.append((x2d, dy2d, [(int(r), int(c)) for r, c in index_list], out, int(block)))
+
+    def flush(self, accumulate: bool = True) -> int:
+        """Launches everything collected so far; returns the number of grouped launches."""
+        problems, self.problems = self.problems, []
+        groups: dict = {}
+        for pr in problems:
+            x2d, dy2d, idx, out, block = pr
+            if len(idx) == 0 or x2d.shape[0] == 0:
+                continue
+            key = (x2d.shape[0], x2d.dtype, out.dtype, block, x2d.device)
+            groups.setdefault(key, []).append(pr)
+        for (T, in_dt, out_dt, block, dev), prs in groups.items():
+            self._launch_group(T, in_dt, out_dt, block, dev, prs, accumulate)
+        return len(groups)
+
+    @staticmethod
+    def _launch_group(T, in_dt, out_dt, block, dev, prs, accumulate) -> None:
+        import numpy as np
+        lib = load()
+        maps: dict = {}
+
+        def map_index(t: torch.Tensor) -> int:
+            key = (t.data_ptr(), t.shape[1], t.stride(0))
+            if key not in maps:
+                maps[key] = (len(maps), t)
+            return maps[key][0]
+
+        esize = prs[0][3].element_size()
+        base_ptr = min(pr[3].data_ptr() for pr in prs)
+        items = []
+        for x2d, dy2d, idx, out, _b in prs:
+            mx, mdy = map_index(x2d), map_index(dy2d)
+            off0 = (out.data_ptr() - base_ptr) // esize
+            # CTAs are scheduled in item order: keep blocks that share a dy strip (same block row) adjacent so that
+            # they run in the same wave and hit each other's lines in L2
+            for i, (r, c) in sorted(enumerate(idx), key=lambda t: (t[1][0], t[1][1])):
+                items.append((mdy, mx, r, c, off0 + i * block * block))
+        n_items, n_maps = len(items), len(maps)
+        item_dt = np.dtype([("map_dy", "<u4"), ("map_x", "<u4"), ("row", "<i4"), ("col", "<i4"), ("out_off", "<i8")])
+        nbytes = n_maps * 128 + n_items * item_dt.itemsize
+        stage = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        host = stage.numpy()
+        in_id = dtype_id(in_dt)
+        for _key, (i, t) in maps.items():
+            check(lib.smt_encode_operand_map(stage.data_ptr() + i * 128, t.data_ptr(), t.shape[1], T, t.stride(0), in_id),
+                  "smt_encode_operand_map")
+        host[n_maps * 128:].view(item_dt)[:] = np.array(items, dtype=item_dt)
+        dev_buf = stage.to(dev, non_blocking=True)
+        ws_bytes = lib.smt_block_grad_gemm_grouped_workspace_bytes(n_items, block, T)
+        ws = _workspace(ws_bytes, dev)
+        with _timed("block_grad_gemm", dev, (n_items, block, T)):
+            check(lib.smt_block_grad_gemm_grouped(dev_buf.data_ptr(), dev_buf.data_ptr() + n_maps * 128, n_items, T, block,
+                                                  in_id, base_ptr, dtype_id(out_dt), 1 if accumulate else 0, ptr(ws),
+                                                  ws_bytes, stream_ptr(dev)), "smt_block_grad_gemm_grouped")
+        _count(2 if ws_bytes > 0 else 1)

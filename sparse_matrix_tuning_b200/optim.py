@@ -166,6 +166,8 @@ class SMTAdam(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        from .smt.smt import flush_block_grads
+        flush_block_grads()                                  # guard: pending grouped block-gradient launches
         clip = self.max_grad_norm > 0.0
         total_sq = None
         if clip:

@@ -28,6 +28,7 @@ non-square weight, so there is nothing well-defined t
 from __future__ import annotations
 
 import re
+import threading
 import weakref
 from typing import Dict, List, Sequence, Tuple
 
@@ -103,6 +104,48 @@ def _block_rc_for(index_list, device) -> torch.Tensor:
     return t
 
 
+# ---- deferred, grouped block-gradient launches (native mode only) ------------------------------------------------
+#
+# With a gradient sink (SMTAdam's flat buffer) nothing has to be RETURNED by linearZ.backward, so the contraction can
+# be postponed: every module's backward only enqueues its (x, dy, blocks, sink) problem and ONE grouped tcgen05
+# launch runs when the autograd engine finishes the backward pass (a queue_callback), i.e. before
+# `loss.backward()` returns.  Per-module launches of ~9-30 blocks cannot fill 148 SMs; the grouped launch of all
+# 869 blocks can.  `flush_block_grads()` is also called by SMTAdam.step() / dp.allreduce_compact_grads as a guard.
+
+_grouped = {"enabled": False}
+_pending = ops.BlockGradBatch()
+_pending_lock = threading.Lock()
+_pending_state = {"callback_queued": False, "stream": None}
+
+
+def set_grouped_backward(enabled: bool) -> None:
+    """Enable / disable deferral of the block-gradient GEMMs to one grouped launch per backward pass."""
+    flush_block_grads()
+    _grouped["enabled"] = bool(enabled)
+
+
+def flush_block_grads() -> int:
+    """Run every pending block-gradient problem now (no-op when nothing is pending)."""
+    with _pending_lock:
+        _pending_state["callback_queued"] = False
+        if len(_pending) == 0:
+            return 0
+        stream = _pending_state["stream"]
+        if stream is not None:
+            with torch.cuda.stream(stream):
+                return _pending.flush(accumulate=True)
+        return _pending.flush(accumulate=True)
+
+
+def _enqueue_block_grad(x2, dy2, index_list, sink, block) -> None:
+    with _pending_lock:
+        _pending.add(x2, dy2, index_list, sink, block)
+        _pending_state["stream"] = torch.cuda.current_stream(x2.device)
+        if not _pending_state["callback_queued"]:
+            _pending_state["callback_queued"] = True
+            torch.autograd.Variable._execution_engine.queue_callback(flush_block_grads)
+
+
 class linearZ(torch.autograd.Function):
     """y = x W^T with a block-sparse weight gradient.  Reference: smt.py:347-413.
 
@@ -137,7 +180,10 @@ class linearZ(torch.autograd.Function):
             sink = getattr(ctx.sw_ref, "_smt_grad_sink", None)
             if sink is not None:
                 # native mode: accumulate straight into the flat (NCCL) gradient buffer, nothing returned
-                ops.block_grad_gemm(x2, dy2, rc, b, out=sink, accumulate=True)
+                if _grouped["enabled"] and dy2.dtype != torch.float32 and n > 0:
+                    _enqueue_block_grad(x2, dy2, ctx.index_list, sink, b)      # one grouped launch per backward
+                else:
+                    ops.block_grad_gemm(x2, dy2, rc, b, out=sink, accumulate=True)
             else:
                 grad_weight = ops.block_grad_gemm(x2, dy2, rc, b, out_dtype=grad_output.dtype)  # smt.py:382-404
                 grad_weight = grad_weight.view(n * b, b)

@@ -153,7 +153,7 @@ def test_topk_segments_and_degenerate_sizes(ops):
 def test_gather_scatter_vs_oracle(ops, block, dtype):
     torch.manual_seed(block)
     w = torch.randn(512, 768).to(dtype)
-    idx = [(1, 2), (0, 0), (512 // block - 1, 768 // block - 1), (0, 1)]
+    idx = [(1, 2), (0, 0), (512 // block - 1, 768 // block - 2), (0, 1)]     # distinct targets for every block size
     wd = w.cuda()
     tab = ops.make_block_table([(wd, r, c) for r, c in idx], "cuda")
     comp = torch.empty(len(idx) * block, block, dtype=dtype, device="cuda")
@@ -318,3 +318,68 @@ def test_warmup_accumulator_vs_capture_loop(ops):
     assert list(H.select_submatrix_based_on_grads(acc_e.grads(), dims, 6).items()) == list(want.items())
     keys, scores = acc_b.scores("mean_abs")
     assert list(H.select_submatrix_from_scores(keys, scores, 6).items()) == list(want.items())
+
+
+@pytest.mark.parametrize("block", [64, 256])
+def test_grouped_gemm_matches_per_problem_launches(ops, block):
+    """Several (x, dy) problems — q/k/v of one layer share x — in ONE grouped launch, accumulated into views of one
+    flat buffer, against the per-problem launches and the fp64 truth."""
+    torch.manual_seed(block)
+    T, fin = 1000, 1024
+    x = torch.randn(T, fin).bfloat16()
+    dys = [torch.randn(T, fo).bfloat16() for fo in (1024, 512, 512)]
+    x2 = torch.randn(T, fin).bfloat16()                              # a second "layer"
+    dy2 = torch.randn(T, 1024).bfloat16()
+    problems = [(x, dys[0], [(0, 1), (2, 3), (1, 1)]), (x, dys[1], [(1, 0)]), (x, dys[2], [(0, 2), (1, 3)]),
+                (x2, dy2, [(3, 0), (0, 0), (2, 2), (1, 2)])]
+    if block == 64:
+        problems = [(a, d, [(r * 2 + 1, c * 3) for r, c in idx]) for a, d, idx in problems]
+    total = sum(len(p[2]) for p in problems)
+    flat = torch.randn(total * block * block, device="cuda")         # pre-existing content: accumulate on top
+    base = flat.clone()
+    batch = ops.BlockGradBatch()
+    xd = {id(x): x.cuda(), id(x2): x2.cuda()}
+    off, views, truths = 0, [], []
+    for a, d, idx in problems:
+        n = len(idx) * block * block
+        view = flat[off:off + n].view(len(idx) * block, block)
+        batch.add(xd[id(a)], d.cuda(), idx, view, block)
+        views.append((off, n))
+        truths.append(O.block_grad_truth(a, d, idx, block))
+        off += n
+    assert batch.flush(accumulate=True) == 1 and len(batch) == 0
+    got = (flat - base).cpu().double()
+    truth = torch.cat([t.reshape(-1) for t in truths])
+    scale = truth.abs().max().item()
+    assert (got - truth).abs().max().item() <= 3e-5 * scale          # fp32 accumulate, fp32 output (+ the fp32 add)
+    for (a, d, idx), (o, n) in zip(problems, views):
+        single = ops.block_grad_gemm(xd[id(a)], d.cuda(), ops.make_block_rc(idx, "cuda"), block, out_dtype=torch.float32)
+        assert (got[o:o + n] - single.cpu().double().reshape(-1)).abs().max().item() <= 3e-5 * scale
+    # bf16 sink, overwrite mode, second flush reuses the object
+    sink = torch.empty(total * block * block, device="cuda", dtype=torch.bfloat16)
+    off = 0
+    for a, d, idx in problems:
+        n = len(idx) * block * block
+        batch.add(xd[id(a)], d.cuda(), idx, sink[off:off + n].view(-1, block), block)
+        off += n
+    batch.flush(accumulate=False)
+    assert (sink.cpu().double() - truth).abs().max().item() <= 2 ** -7 * scale
+
+
+def test_grouped_gemm_large_group_no_split(ops):
+    """A group big enough to need no split-K (>= 148 tiles): whole-block tiles, direct epilogue."""
+    torch.manual_seed(0)
+    T, b = 512, 256
+    xs = [torch.randn(T, 1024, device="cuda").bfloat16() for _ in range(4)]
+    dys = [torch.randn(T, 2560, device="cuda").bfloat16() for _ in range(4)]
+    idx = [(r, c) for r in range(10) for c in range(4)]               # every block of a 2560 x 1024 weight
+    out = torch.zeros(4 * len(idx) * b * b, device="cuda")
+    batch = ops.BlockGradBatch()
+    for i in range(4):
+        batch.add(xs[i], dys[i], idx, out[i * len(idx) * b * b:(i + 1) * len(idx) * b * b].view(-1, b), b)
+    batch.flush(accumulate=False)
+    for i in range(4):
+        ref = dys[i].float().t() @ xs[i].float()                      # the full dense dW^T: every block is a slice of it
+        got = out[i * len(idx) * b * b:(i + 1) * len(idx) * b * b].view(len(idx), b, b)
+        want = torch.stack([ref[r * b:(r + 1) * b, c * b:(c + 1) * b] for r, c in idx])
+        assert (got - want).abs().max().item() <= 2e-5 * want.abs().max().item()

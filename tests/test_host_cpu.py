@@ -60,8 +60,9 @@ def test_plan_is_deterministic_and_bounded(built_library):
     s1 = ops.block_grad_gemm_plan(9, 256, 8192, torch.bfloat16)
     assert s1 == ops.block_grad_gemm_plan(9, 256, 8192, torch.bfloat16)
     splits, ctas = s1
-    assert splits >= 1 and ctas == 9 * splits
-    assert ops.block_grad_gemm_plan(500, 256, 8192, torch.bfloat16)[0] == 1
+    assert splits >= 1 and ctas in (9 * splits, 18 * splits)      # whole-block or half-block tiles
+    assert splits > 1                                             # 9 blocks cannot fill 148 SMs without split-K
+    assert ops.block_grad_gemm_plan(500, 256, 8192, torch.bfloat16) == (1, 500)
     assert ops.block_grad_gemm_plan(3, 64, 64, torch.bfloat16)[0] == 1
     assert ops.block_grad_gemm_plan(3, 128, 512, torch.float32) == (1, 12)
 
