@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--no-ckpt", action="store_true", help="disable gradient checkpointing (reference: on, fine_tune.py:192)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seq", type=int, default=512, help="tokens of the bounded CPU sample")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra no-checkpointing measurement")
     ap.add_argument("--no-group", action="store_true", help="launch the block-gradient GEMM per module instead of grouped")
     return ap.parse_args()
 
@@ -318,10 +319,25 @@ def run_ours(args):
     e3.record()
     barrier()
     ms_e2e = e2.elapsed_time(e3)
+    # ---- extra (reported, not the headline): the same step WITHOUT activation recomputation ------------------------
+    ms_nockpt = None
+    if not args.no_ckpt and not args.no_extra:
+        model.gradient_checkpointing_disable()
+        for i in range(2):
+            step(dev_ids[i])
+        barrier()
+        e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e4.record()
+        for i in range(args.steps):
+            step(dev_ids[args.warmup + i])
+        e5.record()
+        barrier()
+        ms_nockpt = e4.elapsed_time(e5)
     if world > 1:
-        t = torch.tensor([ms_total, ms_e2e], device=device, dtype=torch.float64)
+        t = torch.tensor([ms_total, ms_e2e, ms_nockpt or 0.0], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, ms_e2e = t.tolist()
+        ms_total, ms_e2e, ms_nockpt = t.tolist()
+        ms_nockpt = ms_nockpt or None
 
     if rank != 0:
         if world > 1:
@@ -343,10 +359,25 @@ def run_ours(args):
     gemm_flops = sum(2.0 * tag[1] * tag[1] * tag[2] * tag[0] for _ms, tag in gemm_t)
     n_gemm = len(gemm_t)
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    # minimum HBM bytes of one step's block gradients: every distinct x / dy strip once + the bf16 outputs
+    x_strips = {(k[1], c) for k, idx in sel.items() for _r, c in idx}                 # q/k/v of a layer share x
+    dy_strips = {(k, r) for k, idx in sel.items() for r, _c in idx}
+    gemm_min_bytes = 2.0 * T * BLOCK * (len(x_strips) + len(dy_strips)) + 2.0 * n_blocks * BLOCK * BLOCK
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_bench_gemm_traffic.json")))
+        if args.layers == 32 and not args.no_group:
+            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+    except Exception:
+        pass
     adam_ms = statistics.mean(ms for ms, _ in adam_t) if adam_t else None
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     roofline = {"kernel": "block_grad_umma_kernel<256> (+ splitk_reduce)", "bound": "tensor", "achieved": achieved,
-                "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": None,
+                "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
+                "traffic_note": "dram read+write bytes per launch from one ncu --set full capture of this workload "
+                                "(profiles/r01_bench_gemm_traffic.json); algorithmic minimum in min_hbm_bytes_per_launch",
+                "min_hbm_bytes_per_launch": gemm_min_bytes * args.steps / max(n_gemm, 1),
+                "frac_of_burst_peak": achieved / peaks.get("bf16_tflops", 1599.5),
                 "peak_source": peak_src, "launches": n_gemm, "avg_launch_us": gemm_ms * 1e3 / max(n_gemm, 1),
                 "flops_per_launch": gemm_flops / max(n_gemm, 1), "share_of_step": gemm_ms / ms_total,
                 "also": {"compact_adam": {"bound": "hbm", "avg_ms": adam_ms,
@@ -364,6 +395,7 @@ def run_ours(args):
                        "parallelism": f"dp{world}", "tokens_per_step_per_gpu": T,
                        "l2": "inputs larger than L2 (16 GB of weights streamed per step); no explicit flush",
                        "per_gpu_value": value / world, "loss_last": last,
+                       "tokens_per_s_without_checkpointing": (tokens / (ms_nockpt / 1e3)) if ms_nockpt else None,
                        "warmup_path_ms": {"capture_one_backward": t_capture * 1e3, "scores_topk": t_select * 1e3}},
             "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": B * S * 8, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},

@@ -60,6 +60,8 @@ typedef struct smt_block_ref {
 
 SMT_API const char* smt_last_error(void);
 SMT_API int  smt_version(void);
+/* number of kernels the last smt_block_grad_gemm* call on this thread launched (1, or 2 with a separate reduce) */
+SMT_API int  smt_last_launch_count(void);
 /* sm_count / compute capability of the current device. */
 SMT_API int  smt_device_info(int* sm_count_host, int* cc_major_host, int* cc_minor_host);
 
@@ -122,7 +124,10 @@ SMT_API int smt_block_scatter(const smt_block_ref* table, int n_blocks, int bloc
  * bf16/f16 inputs run the TMA-fed tcgen05/TMEM grouped kernel with fp32 accumulation over all T
  * (one rounding, to `out_dtype`); f32 inputs run an fp32 FMA kernel (exact-order-free, 1e-5 class).
  * `block_rc` is a device int32 [n_blocks][2] table of (row, col).
- * `accumulate` != 0 adds into G instead of overwriting it. */
+ * `accumulate` != 0 adds into G instead of overwriting it.
+ * Workspace contract: the buffer must be ZERO-initialised once when it is allocated and must not be shared with other
+ * entry points or with launches running concurrently on other streams: its first 16 KiB hold split-K arrival counters
+ * that the kernel re-arms itself (all-zero again when the launch completes). */
 SMT_API size_t smt_block_grad_gemm_workspace_bytes(int n_blocks, int block, int64_t T, int in_dtype);
 SMT_API int smt_block_grad_gemm(const void* x, int64_t ldx, int in_features,
                         const void* dy, int64_t lddy, int out_features,

@@ -40,6 +40,7 @@ _P = C.c_void_p
 _SIGNATURES = {
     "smt_last_error": (C.c_char_p, []),
     "smt_version": (C.c_int, []),
+    "smt_last_launch_count": (C.c_int, []),
     "smt_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
     "smt_score_accumulate": (C.c_int, [_P, _P, C.c_int, C.c_int64, _P]),
     "smt_block_sum_accumulate": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int, _P]),

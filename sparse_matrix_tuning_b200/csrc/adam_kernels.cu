@@ -62,11 +62,75 @@ struct AdamArgs {
   float lr, beta1, beta2, eps, wd, bc1, bc2, grad_scale, max_norm;
 };
 
+#ifndef SMT_ADAM_MINB
+#define SMT_ADAM_MINB 5   // resident CTAs per SM the register allocation is tuned for: measured best of {3,4,5,6,8} (profiles/r01_kernels.md)
+#endif
+#ifndef SMT_ADAM_VEC
+#define SMT_ADAM_VEC 4    // elements per thread per iteration (4 or 8); 4 x 5 CTAs/SM beat 8 x 4 by 12 %
+#endif
+constexpr int kAdamVec = SMT_ADAM_VEC;
+
+template <int GDT, int N>
+__device__ __forceinline__ void load_grad(const void* p, int64_t e, float (&g)[N]) {
+  if (GDT == SMT_F32) {
+#pragma unroll
+    for (int q = 0; q < N / 4; ++q) {
+      const float4 a = ld_stream_f4(reinterpret_cast<const float*>(p) + e + 4 * q);
+      g[4 * q] = a.x; g[4 * q + 1] = a.y; g[4 * q + 2] = a.z; g[4 * q + 3] = a.w;
+    }
+  } else if (N == 8) {
+    float t[8];
+    unpack8<GDT>(ld_stream_u4(reinterpret_cast<const uint16_t*>(p) + e), t);
+#pragma unroll
+    for (int j = 0; j < N; ++j) g[j] = t[j];
+  } else {
+    uint2 u;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(u.x), "=r"(u.y)
+                 : "l"(reinterpret_cast<const uint16_t*>(p) + e));
+    if (GDT == SMT_BF16) {
+      g[0] = __uint_as_float(u.x << 16); g[1] = __uint_as_float(u.x & 0xffff0000u);
+      g[2] = __uint_as_float(u.y << 16); g[3] = __uint_as_float(u.y & 0xffff0000u);
+    } else {
+      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+      const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+      g[0] = a.x; g[1] = a.y; g[2] = b.x; g[3] = b.y;
+    }
+  }
+}
+
+template <int N>
+__device__ __forceinline__ void load_state(const float* p, int64_t e, float (&s)[N]) {
+#pragma unroll
+  for (int q = 0; q < N / 4; ++q) {
+    const float4 a = *reinterpret_cast<const float4*>(p + e + 4 * q);   // plain loads: the state is rewritten below
+    s[4 * q] = a.x; s[4 * q + 1] = a.y; s[4 * q + 2] = a.z; s[4 * q + 3] = a.w;
+  }
+}
+
+template <int ODT, int N>
+__device__ __forceinline__ void store_vals(void* base, int64_t e, const float (&p)[N]) {
+  if (ODT == SMT_F32) {
+#pragma unroll
+    for (int q = 0; q < N / 4; ++q)
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + e + 4 * q) =
+          make_float4(p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
+  } else {
+    uint32_t w[N / 2];
+#pragma unroll
+    for (int q = 0; q < N / 2; ++q)
+      w[q] = ODT == SMT_BF16 ? pack_bf16x2(p[2 * q], p[2 * q + 1]) : pack_f16x2(p[2 * q], p[2 * q + 1]);
+    uint16_t* o = reinterpret_cast<uint16_t*>(base) + e;
+    if (N == 8) *reinterpret_cast<uint4*>(o) = make_uint4(w[0], w[1], w[2], w[3]);
+    else *reinterpret_cast<uint2*>(o) = make_uint2(w[0], w[1]);
+  }
+}
+
 template <int GDT, int CDT, int WDT>
-__global__ void __launch_bounds__(kAdamThreads) compact_adam_kernel(
+__global__ void __launch_bounds__(kAdamThreads, SMT_ADAM_MINB) compact_adam_kernel(
     float* __restrict__ master, float* __restrict__ exp_avg, float* __restrict__ exp_avg_sq,
-    const void* __restrict__ grad, int64_t n_vec8, AdamArgs a, const float* __restrict__ sqnorm,
+    const void* __restrict__ grad, int64_t n_vec, AdamArgs a, const float* __restrict__ sqnorm,
     void* __restrict__ compact_out, const smt_block_ref* __restrict__ table, int block_shift) {
+  constexpr int N = kAdamVec;
   // clip coefficient (uniform): deepspeed clip = max_norm / (norm + 1e-6), applied when < 1
   float gscale = a.grad_scale;
   if (sqnorm != nullptr && a.max_norm > 0.f) {
@@ -76,14 +140,15 @@ __global__ void __launch_bounds__(kAdamThreads) compact_adam_kernel(
   }
   const float omb1 = __fsub_rn(1.f, a.beta1), omb2 = __fsub_rn(1.f, a.beta2);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t vec = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; vec < n_vec8; vec += stride) {
-    float g[8], p[8], m[8], v[8];
-    load8<GDT>(grad, vec, g);
-    load8_rw(master, vec, p);  // state is rewritten below: plain (coherent) loads, not ld.global.nc
-    load8_rw(exp_avg, vec, m);
-    load8_rw(exp_avg_sq, vec, v);
+  for (int64_t vec = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; vec < n_vec; vec += stride) {
+    const int64_t e = vec * N;
+    float g[N], p[N], m[N], v[N];
+    load_grad<GDT, N>(grad, e, g);
+    load_state<N>(master, e, p);
+    load_state<N>(exp_avg, e, m);
+    load_state<N>(exp_avg_sq, e, v);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < N; ++j) {
       const float gj = __fmul_rn(g[j], gscale);
       m[j] = __fadd_rn(__fmul_rn(a.beta1, m[j]), __fmul_rn(omb1, gj));
       v[j] = __fadd_rn(__fmul_rn(a.beta2, v[j]), __fmul_rn(__fmul_rn(omb2, gj), gj));
@@ -93,20 +158,19 @@ __global__ void __launch_bounds__(kAdamThreads) compact_adam_kernel(
       const float update = __fadd_rn(__fdiv_rn(mhat, denom), __fmul_rn(a.wd, p[j]));
       p[j] = __fsub_rn(p[j], __fmul_rn(a.lr, update));
     }
-    store8<SMT_F32>(master, vec * 8, p);
-    store8<SMT_F32>(exp_avg, vec * 8, m);
-    store8<SMT_F32>(exp_avg_sq, vec * 8, v);
-    if (compact_out != nullptr) store8<CDT>(compact_out, vec * 8, p);
+    store_vals<SMT_F32, N>(master, e, p);
+    store_vals<SMT_F32, N>(exp_avg, e, m);
+    store_vals<SMT_F32, N>(exp_avg_sq, e, v);
+    if (compact_out != nullptr) store_vals<CDT, N>(compact_out, e, p);
     if (table != nullptr) {
-      // element e = vec*8 lives in block e >> (2*block_shift), at (row, col) inside it
-      const int64_t e = vec * 8;
+      // element e lives in block e >> (2*block_shift), at (row, col) inside it
       const int64_t bi = e >> (2 * block_shift);
       const int within = (int)(e & (((int64_t)1 << (2 * block_shift)) - 1));
       const int r = within >> block_shift, c = within & ((1 << block_shift) - 1);
       const smt_block_ref ref = table[bi];
       const int64_t off = ((int64_t)ref.row << block_shift) * ref.ldw + ((int64_t)ref.col << block_shift) +
                           (int64_t)r * ref.ldw + c;
-      store8<WDT>(reinterpret_cast<void*>(ref.w_ptr), off, p);
+      store_vals<WDT, N>(reinterpret_cast<void*>(ref.w_ptr), off, p);
     }
   }
 }
@@ -231,9 +295,9 @@ extern "C" SMT_API int smt_compact_adam(float* master, float* exp_avg, float* ex
     w_dtype = SMT_BF16;
   }
   AdamArgs a{lr, beta1, beta2, eps, weight_decay, bias_correction1, bias_correction2, grad_scale, max_norm};
-  const int64_t n_vec8 = n_elems / 8;
+  const int64_t n_vec8 = n_elems / kAdamVec;       // vectors of kAdamVec elements (n_elems is a multiple of 8)
   int64_t want = (n_vec8 + kAdamThreads - 1) / kAdamThreads;
-  const int64_t cap = (int64_t)sm_count() * 8;
+  const int64_t cap = (int64_t)sm_count() * SMT_ADAM_MINB * 2;
   const int grid = (int)(want < cap ? want : cap);
   cudaStream_t st = (cudaStream_t)stream;
   if (grad_dtype == SMT_F32) return launch_adam_c<SMT_F32>(compact_dtype, w_dtype, grid, st, master, exp_avg, exp_avg_sq, grad, n_vec8, a, sqnorm, compact_out, table, shift);

@@ -39,6 +39,7 @@ constexpr int kGemmThreads = 64 + 32 * kEpiWarps;   // warp 0 TMA, warp 1 MMA + 
 constexpr int kSmemBudget = 200 * 1024;       // pipeline stages (dynamic smem), leaves room for barriers
 constexpr int kMinKTilesPerSplit = 4;
 constexpr int kStageRow = 36;                 // floats per row of the epilogue transpose buffer (32 + 4 pad)
+constexpr size_t kCounterBytes = 16384;       // head of the workspace: self-resetting split-K arrival counters
 
 template <int B, int MH_>
 struct Cfg {
@@ -171,6 +172,7 @@ struct GemmParams {
   const CUtensorMap* maps;        // grouped: tensor maps in global memory (indexed by the items)
   void* out;                      // G base (single problem: block i at i*b*b; grouped: items[i].out_off)
   float* ws;                      // fp32 partial tiles when splits > 1
+  int* counters;                  // fused reduction: 2 self-resetting ints per tile (NULL = separate reduce kernel)
   int splits;
   int kt_total;                   // number of K tiles = ceil(T / kKTile)
   int kt_per_split;
@@ -227,6 +229,43 @@ __device__ __forceinline__ void store_subtile(float* stage, const uint32_t (&r)[
     store4<ODT, ACC>(out_base, off00 + (int64_t)row * ld + cv, v);
   }
   __syncwarp();
+}
+
+__device__ __forceinline__ float4 ld_cg_f4(const float* p) {   // L2-coherent load (data written by other CTAs of this grid)
+  float4 r;
+  asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Fused split-K reduction (cooperative launch: every CTA of the grid is resident, so waiting on siblings is safe).
+// Each of the `splits` CTAs of a tile has written its fp32 partial; after a per-tile arrival counter reaches
+// `splits`, CTA `split` sums ITS slice of the tile over all partials in the fixed order 0..splits-1 and writes the
+// final output.  The last CTA to finish resets the two counters, so the buffer is all-zero again at kernel end.
+template <int ODT>
+__device__ __forceinline__ void fused_reduce_slice(const float* __restrict__ part0, int splits, int tile_elems,
+                                                   int e_begin, int e_end, void* out, int64_t out_off, bool acc_out) {
+  for (int e = e_begin + (int)threadIdx.x * 8; e < e_end; e += (int)blockDim.x * 8) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int sp = 0; sp < splits; ++sp) {
+      const float* src = part0 + (int64_t)sp * tile_elems + e;
+      const float4 a = ld_cg_f4(src), b = ld_cg_f4(src + 4);
+      acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
+      acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+    }
+    const int64_t o = out_off + e;
+    if (acc_out) {
+      store4<ODT, true>(out, o, make_float4(acc[0], acc[1], acc[2], acc[3]));
+      store4<ODT, true>(out, o + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
+    } else {
+      store4<ODT, false>(out, o, make_float4(acc[0], acc[1], acc[2], acc[3]));
+      store4<ODT, false>(out, o + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
+    }
+  }
 }
 
 template <int B, int MH, bool GROUPED>
@@ -374,6 +413,39 @@ __global__ void __launch_bounds__(kGemmThreads, 1) block_grad_umma_kernel(
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+
+  if (p.counters != nullptr) {
+    // ===== fused split-K reduction =====
+    __threadfence();                     // this thread's partial-tile stores are visible device-wide ...
+    __syncthreads();                     // ... for every thread of the CTA, before the CTA announces itself
+    int* arrive = p.counters + 2 * tile;
+    if (threadIdx.x == 0) {
+      atomicAdd(arrive, 1);
+      const long long t0 = clock64();
+      while (ld_acquire_gpu(arrive) < p.splits) {
+        __nanosleep(64);
+        if (clock64() - t0 > 4000000000ll) {
+          printf("smt_block_grad_gemm: split-K arrival wait timed out (tile %d split %d)\n", tile, split);
+          __trap();
+        }
+      }
+    }
+    __syncthreads();
+    const int chunk = ((C::TILE_ELEMS / 8 + p.splits - 1) / p.splits) * 8;
+    const int e_begin = split * chunk;
+    const int e_end = min(e_begin + chunk, C::TILE_ELEMS);
+    const float* part0 = p.ws + (int64_t)tile * p.splits * C::TILE_ELEMS;
+    if (p.out_dtype == SMT_F32) fused_reduce_slice<SMT_F32>(part0, p.splits, C::TILE_ELEMS, e_begin, e_end, p.out, out_off, p.accumulate != 0);
+    else if (p.out_dtype == SMT_BF16) fused_reduce_slice<SMT_BF16>(part0, p.splits, C::TILE_ELEMS, e_begin, e_end, p.out, out_off, p.accumulate != 0);
+    else fused_reduce_slice<SMT_F16>(part0, p.splits, C::TILE_ELEMS, e_begin, e_end, p.out, out_off, p.accumulate != 0);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      if (atomicAdd(arrive + 1, 1) == p.splits - 1) {   // every sibling has passed its wait: safe to re-arm
+        arrive[0] = 0;
+        arrive[1] = 0;
+      }
+    }
   }
 }
 
@@ -536,7 +608,8 @@ Plan make_plan(int n_blocks, int block, int64_t T) {
       const long waves = (ctas + sms - 1) / sms;
       const double epi = tile_bytes / 131072.0 * (s_eff > 1 ? 2.0 : 1.0);
       double cost = 4.0 + waves * (5.0 + kt * c_kt + epi);
-      if (s_eff > 1) cost += 8.0 + (double)ctas * tile_bytes / 4.0e6;
+      // one wave => the reduction is fused into the GEMM kernel (cooperative launch); else a second kernel
+      if (s_eff > 1) cost += (ctas <= sms ? 3.0 : 8.0) + (double)ctas * tile_bytes / 4.0e6;
       if (cost < best_cost) {
         best_cost = cost;
         best.mh = mh; best.tiles = tiles; best.splits = s_eff; best.kt_total = kt_total; best.kt_per_split = kt;
@@ -591,6 +664,13 @@ int launch_umma_cfg(const CUtensorMap& mx, const CUtensorMap& mdy, const GemmPar
   auto kern = block_grad_umma_kernel<B, MH, GROUPED>;
   SMT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   dim3 grid(pl.tiles, pl.splits);
+  if (gp.counters != nullptr) {
+    // fused reduction: CTAs wait on their siblings, which is only legal when all of them are co-resident
+    void* args[3] = {const_cast<CUtensorMap*>(&mx), const_cast<CUtensorMap*>(&mdy), const_cast<GemmParams*>(&gp)};
+    SMT_CHECK_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kern), grid, dim3(kGemmThreads), args,
+                                               (size_t)C::SMEM_BYTES, st));
+    return SMT_OK;
+  }
   kern<<<grid, kGemmThreads, C::SMEM_BYTES, st>>>(mx, mdy, gp);
   SMT_CHECK_LAUNCH();
   return SMT_OK;
@@ -638,7 +718,19 @@ int launch_reduce(const float* ws, void* out, const smt_gemm_item* items, int bl
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 size_t plan_workspace_bytes(const Plan& pl) {
-  return pl.splits > 1 ? (size_t)pl.tiles * pl.splits * pl.tile_elems * sizeof(float) : 0;
+  return pl.splits > 1 ? kCounterBytes + (size_t)pl.tiles * pl.splits * pl.tile_elems * sizeof(float) : 0;
+}
+
+// The fused (in-kernel) reduction needs every CTA resident at once: one CTA per SM (shared memory), one wave.
+bool use_fused_reduce(const Plan& pl) {
+  if (pl.splits <= 1 || env_int("SMT_GEMM_NO_FUSED_REDUCE", 0)) return false;
+  static int coop = -1;
+  if (coop < 0) {
+    int dev = 0, v = 0;
+    coop = (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess && v) ? 1 : 0;
+  }
+  return coop == 1 && (long)pl.tiles * pl.splits <= sm_count() && (size_t)pl.tiles * 2 * sizeof(int) <= kCounterBytes;
 }
 
 }  // namespace
@@ -704,6 +796,7 @@ extern "C" SMT_API int smt_block_grad_gemm(const void* x, int64_t ldx, int in_fe
     else if (out_dtype == SMT_BF16) block_grad_f32_kernel<SMT_BF16><<<grid, 256, 0, st>>>(xf, ldx, dyf, lddy, T, block_rc, block, G, accumulate);
     else block_grad_f32_kernel<SMT_F16><<<grid, 256, 0, st>>>(xf, ldx, dyf, lddy, T, block_rc, block, G, accumulate);
     SMT_CHECK_LAUNCH();
+    set_launch_count(1);
     return SMT_OK;
   }
 
@@ -723,7 +816,8 @@ extern "C" SMT_API int smt_block_grad_gemm(const void* x, int64_t ldx, int in_fe
   GemmParams gp{};
   gp.block_rc = block_rc;
   gp.out = G;
-  gp.ws = reinterpret_cast<float*>(workspace);
+  gp.ws = need > 0 ? reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + kCounterBytes) : nullptr;
+  gp.counters = use_fused_reduce(pl) ? reinterpret_cast<int*>(workspace) : nullptr;
   gp.splits = pl.splits;
   gp.kt_total = pl.kt_total;
   gp.kt_per_split = pl.kt_per_split;
@@ -731,7 +825,11 @@ extern "C" SMT_API int smt_block_grad_gemm(const void* x, int64_t ldx, int in_fe
   gp.accumulate = accumulate;
   gp.in_fmt = in_dtype == SMT_BF16 ? 1 : 0;
   if (int rc = launch_umma<false>(block, mx, mdy, gp, pl, st)) return rc;
-  if (pl.splits > 1) return launch_reduce(gp.ws, G, nullptr, block, pl, n_blocks, out_dtype, accumulate, st);
+  set_launch_count(1);
+  if (pl.splits > 1 && gp.counters == nullptr) {
+    set_launch_count(2);
+    return launch_reduce(gp.ws, G, nullptr, block, pl, n_blocks, out_dtype, accumulate, st);
+  }
   return SMT_OK;
 }
 
@@ -777,7 +875,8 @@ extern "C" SMT_API int smt_block_grad_gemm_grouped(const void* maps, const smt_g
   gp.items = items;
   gp.maps = reinterpret_cast<const CUtensorMap*>(maps);
   gp.out = out_base;
-  gp.ws = reinterpret_cast<float*>(workspace);
+  gp.ws = need > 0 ? reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + kCounterBytes) : nullptr;
+  gp.counters = use_fused_reduce(pl) ? reinterpret_cast<int*>(workspace) : nullptr;
   gp.splits = pl.splits;
   gp.kt_total = pl.kt_total;
   gp.kt_per_split = pl.kt_per_split;
@@ -787,6 +886,10 @@ extern "C" SMT_API int smt_block_grad_gemm_grouped(const void* maps, const smt_g
   CUtensorMap dummy;
   memset(&dummy, 0, sizeof(dummy));
   if (int rc = launch_umma<true>(block, dummy, dummy, gp, pl, st)) return rc;
-  if (pl.splits > 1) return launch_reduce(gp.ws, out_base, items, block, pl, n_items, out_dtype, accumulate, st);
+  set_launch_count(1);
+  if (pl.splits > 1 && gp.counters == nullptr) {
+    set_launch_count(2);
+    return launch_reduce(gp.ws, out_base, items, block, pl, n_items, out_dtype, accumulate, st);
+  }
   return SMT_OK;
 }

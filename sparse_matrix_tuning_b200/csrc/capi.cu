@@ -7,7 +7,9 @@
 namespace smt {
 namespace {
 thread_local char g_err[512] = "";
+thread_local int g_launches = 0;
 }
+void set_launch_count(int n) { g_launches = n; }
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -17,6 +19,8 @@ void set_error(const char* fmt, ...) {
 }  // namespace smt
 
 extern "C" SMT_API const char* smt_last_error(void) { return smt::g_err; }
+
+extern "C" SMT_API int smt_last_launch_count(void) { return smt::g_launches; }
 
 extern "C" SMT_API int smt_version(void) { return 100; /* 0.1.0 */ }
 

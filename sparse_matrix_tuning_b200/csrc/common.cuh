@@ -14,6 +14,7 @@
 namespace smt {
 
 void set_error(const char* fmt, ...);
+void set_launch_count(int n);   // kernels launched by the last GEMM entry point on this thread
 
 #define SMT_CHECK_ARG(cond, ...)                    \
   do {                                              \

@@ -219,14 +219,16 @@ def block_scatter(table: torch.Tensor, n_blocks: int, block: int, compact: torch
 _ws_cache: dict = {}
 
 
-def _workspace(nbytes: int, device) -> Optional[torch.Tensor]:
-    """Grow-only per-(device, stream) scratch buffer (allocation stays out of the C library)."""
+def _workspace(nbytes: int, device, tag: str = "gemm") -> Optional[torch.Tensor]:
+    """Grow-only per-(purpose, device, stream) scratch buffer (allocation stays out of the C library).  Buffers are
+    ZERO-initialised when (re)allocated: the GEMM keeps self-resetting split-K arrival counters in the first 16 KiB
+    of its workspace (see smt_block_grad_gemm in include/smt_b200.h)."""
     if nbytes == 0:
         return None
-    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    key = (tag, device, torch.cuda.current_stream(device).cuda_stream)
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.empty((nbytes,), dtype=torch.uint8, device=device)
+        buf = torch.zeros((nbytes,), dtype=torch.uint8, device=device)
         _ws_cache[key] = buf
     return buf
 
@@ -259,7 +261,7 @@ def block_grad_gemm(x2d: torch.Tensor, dy2d: torch.Tensor, block_rc: torch.Tenso
                                       1 if accumulate else 0, ptr(ws), ws_bytes, _st(x2d)),
               "smt_block_grad_gemm")
     if n > 0 and T > 0:
-        _count(2 if ws_bytes > 0 else 1)
+        _count(lib.smt_last_launch_count())
     return out
 
 
@@ -280,7 +282,7 @@ def grad_sqnorm(grad: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch
         out = torch.empty((1,), dtype=torch.float32, device=grad.device)
     lib = load()
     ws_bytes = lib.smt_grad_sqnorm_workspace_bytes()
-    ws = _workspace(ws_bytes, grad.device)
+    ws = _workspace(ws_bytes, grad.device, tag="sqnorm")
     check(lib.smt_grad_sqnorm(ptr(grad), dtype_id(grad.dtype), grad.numel(), ptr(out), ptr(ws), ws_bytes,
                               _st(grad)), "smt_grad_sqnorm")
     _count(2)
@@ -388,4 +390,4 @@ class BlockGradBatch:
             check(lib.smt_block_grad_gemm_grouped(dev_buf.data_ptr(), dev_buf.data_ptr() + n_maps * 128, n_items, T, block,
                                                   in_id, base_ptr, dtype_id(out_dt), 1 if accumulate else 0, ptr(ws),
                                                   ws_bytes, stream_ptr(dev)), "smt_block_grad_gemm_grouped")
-        _count(2 if ws_bytes > 0 else 1)
+        _count(lib.smt_last_launch_count())

@@ -134,17 +134,32 @@ class SMTAdam(torch.optim.Optimizer):
                                  "master": arena.master[off:off + n].view(p.shape)}
 
     def load_state_dict(self, state_dict):
-        views = {id(p): dict(self.state[p]) for p in self.state}
-        super().load_state_dict(state_dict)
-        # copy the loaded tensors back INTO the arena views (super() replaced them by fresh tensors)
-        for group in self.param_groups:
-            for p in group["params"]:
-                if id(p) in views and p in self.state:
-                    loaded = self.state[p]
-                    for name, view in views[id(p)].items():
-                        if name in loaded and torch.is_tensor(loaded[name]):
-                            view.copy_(loaded[name])
-                    self.state[p] = views[id(p)]
+        """Restores hyper-parameters and state IN PLACE.  torch's generic implementation would cast every state tensor
+        to the parameter dtype (bf16) and replace the arena views by fresh tensors; the fp32 masters and moments must
+        keep their precision and their storage."""
+        saved_groups, saved_state = state_dict["param_groups"], state_dict["state"]
+        if len(saved_groups) != len(self.param_groups):
+            raise ValueError("loaded state dict has a different number of parameter groups")
+        id_map = {}
+        for sg, g in zip(saved_groups, self.param_groups):
+            if len(sg["params"]) != len(g["params"]):
+                raise ValueError("loaded state dict contains a parameter group that doesn't match the size of optimizer's group")
+            for pid, p in zip(sg["params"], g["params"]):
+                id_map[pid] = p
+            for k, v in sg.items():
+                if k != "params":
+                    g[k] = v
+        for pid, st in saved_state.items():
+            p = id_map[pid]
+            mine = self.state[p]
+            for name, val in st.items():
+                if torch.is_tensor(val):
+                    if name in mine and torch.is_tensor(mine[name]):
+                        mine[name].copy_(val.reshape(mine[name].shape))       # into the arena view, fp32 preserved
+                    else:
+                        mine[name] = val.detach().clone().to(p.device)
+                else:
+                    mine[name] = val
 
     def zero_grad(self, set_to_none: bool = False):
         """Zeroes the flat gradient buffers in place (the views stay attached, so nothing is re-pointed)."""
@@ -229,7 +244,12 @@ class SMTAdam(torch.optim.Optimizer):
         if "exp_avg" not in st:
             st["exp_avg"] = torch.zeros(n, dtype=torch.float32, device=p.device)
             st["exp_avg_sq"] = torch.zeros(n, dtype=torch.float32, device=p.device)
-            st["master"] = p.data.reshape(-1) if p.dtype == torch.float32 else p.data.reshape(-1).float()
+        if p.dtype == torch.float32:
+            master = p.data.reshape(-1)                      # fp32 parameters are their own master
+        else:
+            if "master" not in st:
+                st["master"] = p.data.reshape(-1).float()
+            master = st["master"]
         g = p.grad.contiguous().reshape(-1)
         out = None if p.dtype == torch.float32 else p.data.reshape(-1)
         owner = _owner_of(p)
@@ -237,7 +257,7 @@ class SMTAdam(torch.optim.Optimizer):
         if owner is not None:
             kw.update(table=owner._block_table(), n_blocks=len(owner.index_list), block=owner.block,
                       w_dtype=owner.weight.dtype)
-        ops.compact_adam(st["master"], st["exp_avg"], st["exp_avg_sq"], g, compact_out=out, **kw)
+        ops.compact_adam(master, st["exp_avg"].reshape(-1), st["exp_avg_sq"].reshape(-1), g, compact_out=out, **kw)
         if owner is not None:
             owner.mark_synced()
         else:

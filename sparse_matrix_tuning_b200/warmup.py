@@ -68,6 +68,32 @@ class WarmupGradAccumulator:
             self.add(key, g.detach())
         self.steps += 1
 
+    def attach(self, model, free_grads: bool = False):
+        """Hook mode: accumulate each targeted gradient the moment autograd has finished
+        producing it (`register_post_accumulate_grad_hook`) instead of sweeping all parameters after backward.
+        With `free_grads=True` the parameter's `.grad` is released right away, so a capture-only warm-up pass never
+        holds more than one targeted gradient at a time.  Returns the hook handles (call `.remove()` on each, or
+        `detach()`)."""
+        self._handles = []
+        for name, p in model.named_parameters():
+            key = classify_parameter(name, self.mlp, self.attention)
+            if key is None or not p.requires_grad:
+                continue
+
+            def hook(param, key=key):
+                if param.grad is not None:
+                    self.add(key, param.grad.detach())
+                    if free_grads:
+                        param.grad = None
+
+            self._handles.append(p.register_post_accumulate_grad_hook(hook))
+        return self._handles
+
+    def detach(self) -> None:
+        for h in getattr(self, "_handles", []):
+            h.remove()
+        self._handles = []
+
     def add(self, key: Key, grad: torch.Tensor) -> None:
         if not grad.is_cuda:
             raise SMTLibraryError("WarmupGradAccumulator works on CUDA gradients (no CPU path)")

@@ -245,3 +245,81 @@ def test_grouped_backward_equals_per_module_backward(api):
         assert l1 == l0
         assert (g1 - g0).abs().max().item() <= 2 ** -7 * g0.abs().max().item()   # bf16 grads, different split-K plans
         assert (p1 - p0).abs().max().item() <= 2.1e-3                            # one Adam step of lr 1e-3 (sign flips of ~0 grads)
+
+
+def test_merged_export_and_resume(api):
+    """a merged HF-format state dict reproduces the SMT model's logits in an UNMODIFIED
+    LlamaForCausalLM, and (index lists + compact params + optimizer state) round-trip for a bit-exact resume."""
+    M, _H = api
+    from transformers import LlamaConfig, LlamaForCausalLM
+    from sparse_matrix_tuning_b200 import checkpoint as CK
+    from sparse_matrix_tuning_b200.optim import SMTAdam
+    cfg = LlamaConfig(vocab_size=512, hidden_size=512, intermediate_size=1024, num_hidden_layers=2,
+                      num_attention_heads=8, num_key_value_heads=4, max_position_embeddings=128)
+    sel = {("q_proj", 0): [(1, 0), (0, 1)], ("v_proj", 1): [(0, 1)]}
+
+    def build():
+        torch.manual_seed(3)
+        model = LlamaForCausalLM(cfg).cuda().bfloat16()
+        M.freeze_unselected_matrix_layer(model, {}, sel)
+        M.convert_linear_layer_to_matrix_sparsity(model, {}, sel)
+        opt = SMTAdam(M.get_optimizer_sparse_grouped_parameters(model, 0.0, 1e-3), betas=(0.9, 0.95), max_grad_norm=1.0)
+        return model, opt
+
+    ids = torch.randint(0, 512, (2, 64), generator=torch.Generator().manual_seed(4)).cuda()
+
+    def train(model, opt, steps):
+        for _ in range(steps):
+            opt.zero_grad()
+            model(input_ids=ids, labels=ids, use_cache=False).loss.backward()
+            opt.step()
+
+    model, opt = build()
+    train(model, opt, 2)
+    merged = CK.merged_state_dict(model)
+    assert not any(k.endswith("selected_weight") for k in merged)
+    torch.manual_seed(99)
+    plain = LlamaForCausalLM(cfg).cuda().bfloat16()
+    plain.load_state_dict(merged)
+    with torch.no_grad():
+        assert torch.equal(plain(input_ids=ids).logits, model(input_ids=ids).logits)
+    # resume: state saved after 2 steps, restored into a fresh conversion, one more step on both == identical
+    state = CK.smt_state(model, opt)
+    assert CK.selection_from_state(state) == ({}, {k: list(v) for k, v in sel.items()})
+    model2, opt2 = build()
+    CK.load_smt_state(model2, state, opt2)
+    train(model, opt, 1)
+    train(model2, opt2, 1)
+    for (n1, p1), (n2, p2) in zip(model.named_parameters(), model2.named_parameters()):
+        assert n1 == n2 and torch.equal(p1, p2), n1
+    for a, b in zip(opt._arenas, opt2._arenas):
+        assert torch.equal(a.master, b.master) and torch.equal(a.exp_avg, b.exp_avg) and torch.equal(a.exp_avg_sq, b.exp_avg_sq)
+
+
+def test_warmup_hook_mode_matches_post_backward_sweep(api):
+    """Grad-ready hooks (with immediate release of .grad) accumulate exactly what the reference's post-backward sweep
+    (fine_tune.py:716-768) accumulates."""
+    _M, H = api
+    from transformers import LlamaConfig, LlamaForCausalLM
+    from sparse_matrix_tuning_b200.warmup import WarmupGradAccumulator
+    torch.manual_seed(0)
+    cfg = LlamaConfig(vocab_size=512, hidden_size=512, intermediate_size=1024, num_hidden_layers=2,
+                      num_attention_heads=8, num_key_value_heads=4, max_position_embeddings=128)
+    model = LlamaForCausalLM(cfg).cuda().bfloat16()
+    ids = [torch.randint(0, 512, (2, 64), generator=torch.Generator().manual_seed(s)).cuda() for s in (1, 2)]
+    sweep = WarmupGradAccumulator(block=256, mode="elementwise", mlp=True)
+    for b in ids:
+        model.zero_grad(set_to_none=True)
+        model(input_ids=b, labels=b, use_cache=False).loss.backward()
+        sweep.accumulate(model.named_parameters())
+    hooked = WarmupGradAccumulator(block=256, mode="elementwise", mlp=True)
+    hooked.attach(model, free_grads=True)
+    for b in ids:
+        model.zero_grad(set_to_none=True)
+        model(input_ids=b, labels=b, use_cache=False).loss.backward()
+    hooked.detach()
+    assert set(sweep.grads()) == set(hooked.grads()) and len(sweep.grads()) == 2 * 6
+    for k in sweep.grads():
+        assert torch.equal(sweep.grads()[k], hooked.grads()[k]), k
+    assert model.model.layers[0].self_attn.q_proj.weight.grad is None        # released by the hook
+    assert model.model.layers[0].self_attn.o_proj.weight.grad is not None    # not a captured module
