@@ -366,7 +366,7 @@ def run_ours(args):
     traffic = None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "r01_bench_gemm_traffic.json")))
-        if args.layers == 32 and not args.no_group:
+        if args.layers == 32 and not args.no_group and world == 1:
             traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
     except Exception:
         pass

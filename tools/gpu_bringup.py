@@ -2,8 +2,8 @@
 prints PASS/FAIL per case plus rough timings.  Each group runs in its own subprocess so that a device
 trap in one kernel cannot poison the CUDA context of the others.
 
-    python tests/gpu_bringup.py            # all groups
-    python tests/gpu_bringup.py gemm       # one group
+    python tools/gpu_bringup.py            # all groups
+    python tools/gpu_bringup.py gemm       # one group
 """
 import os
 import subprocess
