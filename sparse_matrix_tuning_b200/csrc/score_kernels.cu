@@ -16,22 +16,54 @@ constexpr int kThreads = 256;
 
 // ---- acc += grad ---------------------------------------------------------------------------
 
+#ifndef SMT_SCORE_UNROLL
+#define SMT_SCORE_UNROLL 2     // vec8 groups in flight per thread (measured best of {1, 2, 4}: profiles/r01_kernels.md)
+#endif
+#ifndef SMT_SCORE_CTAS
+#define SMT_SCORE_CTAS 8       // grid cap in CTAs per SM for the streaming kernels
+#endif
+
+template <int DT>
+__device__ __forceinline__ void load_grad8(const void* __restrict__ grad, int64_t i, float (&g)[8]) {
+  if (DT == SMT_F32) {
+    const float4 a = ld_stream_f4(reinterpret_cast<const float4*>(grad) + 2 * i);
+    const float4 b = ld_stream_f4(reinterpret_cast<const float4*>(grad) + 2 * i + 1);
+    g[0] = a.x; g[1] = a.y; g[2] = a.z; g[3] = a.w;
+    g[4] = b.x; g[5] = b.y; g[6] = b.z; g[7] = b.w;
+  } else {
+    unpack8<DT>(ld_stream_u4(reinterpret_cast<const uint4*>(grad) + i), g);
+  }
+}
+
 template <int DT>
 __global__ void __launch_bounds__(kThreads) score_accumulate_vec_kernel(
     float* __restrict__ acc, const void* __restrict__ grad, int64_t n_vec8) {
   // one "vec8" = 8 consecutive elements: 32 B of fp32 accumulator, 16 B (16-bit) or 32 B (fp32) of grad
+  constexpr int U = SMT_SCORE_UNROLL;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec8; i += stride) {
-    float g[8];
-    if (DT == SMT_F32) {
-      const float4 a = ld_stream_f4(reinterpret_cast<const float4*>(grad) + 2 * i);
-      const float4 b = ld_stream_f4(reinterpret_cast<const float4*>(grad) + 2 * i + 1);
-      g[0] = a.x; g[1] = a.y; g[2] = a.z; g[3] = a.w;
-      g[4] = b.x; g[5] = b.y; g[6] = b.z; g[7] = b.w;
-    } else {
-      const uint4 u = ld_stream_u4(reinterpret_cast<const uint4*>(grad) + i);
-      unpack8<DT>(u, g);
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i + (U - 1) * stride < n_vec8; i += U * stride) {
+    float g[U][8];
+    float4 a0[U], a1[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {                       // all loads first: U x 48 B in flight per thread
+      load_grad8<DT>(grad, i + u * stride, g[u]);
+      const float4* ap = reinterpret_cast<const float4*>(acc) + 2 * (i + u * stride);
+      a0[u] = ap[0];
+      a1[u] = ap[1];
     }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float4* ap = reinterpret_cast<float4*>(acc) + 2 * (i + u * stride);
+      a0[u].x += g[u][0]; a0[u].y += g[u][1]; a0[u].z += g[u][2]; a0[u].w += g[u][3];
+      a1[u].x += g[u][4]; a1[u].y += g[u][5]; a1[u].z += g[u][6]; a1[u].w += g[u][7];
+      ap[0] = a0[u];
+      ap[1] = a1[u];
+    }
+  }
+  for (; i < n_vec8; i += stride) {                     // remainder
+    float g[8];
+    load_grad8<DT>(grad, i, g);
     float4* ap = reinterpret_cast<float4*>(acc) + 2 * i;
     float4 a0 = ap[0], a1 = ap[1];
     a0.x += g[0]; a0.y += g[1]; a0.z += g[2]; a0.w += g[3];
@@ -205,7 +237,7 @@ __global__ void __launch_bounds__(kThreads) channel_score_reduce_kernel(
 inline int streaming_grid(int64_t work_items) {
   // enough CTAs for ~8 resident per SM, capped by the work
   int64_t want = (work_items + kThreads - 1) / kThreads;
-  int64_t cap = (int64_t)sm_count() * 8;
+  int64_t cap = (int64_t)sm_count() * SMT_SCORE_CTAS;
   return (int)(want < cap ? (want < 1 ? 1 : want) : cap);
 }
 

@@ -323,3 +323,50 @@ def test_warmup_hook_mode_matches_post_backward_sweep(api):
         assert torch.equal(sweep.grads()[k], hooked.grads()[k]), k
     assert model.model.layers[0].self_attn.q_proj.weight.grad is None        # released by the hook
     assert model.model.layers[0].self_attn.o_proj.weight.grad is not None    # not a captured module
+
+
+def test_linearz_layouts_and_direct_apply(api):
+    """linearZ.apply called directly (as the reference's fwbwTest does, smt.py:865-903), 2-D and 4-D inputs, and a
+    NON-contiguous grad_output (transposed producer) — all must give the dense-slice gradients."""
+    M, _H = api
+    torch.manual_seed(5)
+    w = torch.nn.Parameter(torch.randn(512, 768, device="cuda").bfloat16() * 0.05)
+    idx = [(1, 2), (0, 0), (1, 0)]
+    layer = M.LinearLayer_MatrixSparsity(w, index_list=idx)
+    for shape in ((40, 768), (2, 3, 8, 768), (3, 16, 768)):
+        x = torch.randn(*shape, device="cuda").bfloat16().requires_grad_(True)
+        layer.selected_weight.grad = None
+        y = M.linearZ.apply(x, layer.selected_weight, idx, layer.weight)
+        assert y.shape == shape[:-1] + (512,)
+        g = torch.randn(512, x.numel() // 768, device="cuda").bfloat16().t().reshape(y.shape)   # non-contiguous rows
+        assert not g.reshape(-1, 512).is_contiguous() or len(shape) > 2
+        y.backward(g)
+        x2, g2 = x.detach().reshape(-1, 768).float(), g.reshape(-1, 512).float()
+        dense = g2.t() @ x2                                                               # full dW = dy^T x
+        want = torch.cat([dense[r * 256:(r + 1) * 256, c * 256:(c + 1) * 256] for r, c in idx])
+        got = layer.selected_weight.grad.float()
+        assert got.shape == (3 * 256, 256)
+        assert (got - want).abs().max().item() <= 2 ** -7 * want.abs().max().item()
+        assert (x.grad.float() - (g2 @ w.detach().float()).reshape(shape)).abs().max().item() <= \
+            2 ** -6 * x.grad.float().abs().max().item()
+
+
+def test_gradient_accumulation_over_micro_batches(api):
+    """Two backward passes without zero_grad accumulate into the flat gradient buffer, like autograd does."""
+    M, _H = api
+    from sparse_matrix_tuning_b200.optim import SMTAdam
+    torch.manual_seed(6)
+    w = torch.nn.Parameter(torch.randn(256, 512, device="cuda").bfloat16() * 0.05)
+    layer = M.LinearLayer_MatrixSparsity(w, index_list=[(0, 1)])
+    opt = SMTAdam([layer.selected_weight], lr=1e-3)
+    xs = [torch.randn(2, 64, 512, device="cuda").bfloat16() for _ in range(2)]
+    gs = [torch.randn(2, 64, 256, device="cuda").bfloat16() for _ in range(2)]
+    opt.zero_grad()
+    for x, g in zip(xs, gs):
+        layer(x).backward(g)
+    want = sum(g.reshape(-1, 256).float().t() @ x.reshape(-1, 512).float()[:, 256:512] for x, g in zip(xs, gs))
+    got = layer.selected_weight.grad.float()
+    assert got.data_ptr() == opt.flat_grads()[0].data_ptr()                 # .grad IS the flat (NCCL) buffer
+    assert (got - want).abs().max().item() <= 2 ** -6 * want.abs().max().item()
+    opt.zero_grad()
+    assert not opt.flat_grads()[0].any()
