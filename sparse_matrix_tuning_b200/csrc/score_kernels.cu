@@ -20,7 +20,7 @@ constexpr int kThreads = 256;
 #define SMT_SCORE_UNROLL 2     // vec8 groups in flight per thread (measured best of {1, 2, 4}: profiles/r01_kernels.md)
 #endif
 #ifndef SMT_SCORE_CTAS
-#define SMT_SCORE_CTAS 8       // grid cap in CTAs per SM for the streaming kernels
+#define SMT_SCORE_CTAS 4       // grid cap in CTAs per SM for the streaming kernels (2 x 4 measured best: 6 125 GB/s)
 #endif
 
 template <int DT>

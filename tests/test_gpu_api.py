@@ -366,7 +366,7 @@ def test_gradient_accumulation_over_micro_batches(api):
         layer(x).backward(g)
     want = sum(g.reshape(-1, 256).float().t() @ x.reshape(-1, 512).float()[:, 256:512] for x, g in zip(xs, gs))
     got = layer.selected_weight.grad.float()
-    assert got.data_ptr() == opt.flat_grads()[0].data_ptr()                 # .grad IS the flat (NCCL) buffer
+    assert layer.selected_weight.grad.data_ptr() == opt.flat_grads()[0].data_ptr()   # .grad IS the flat (NCCL) buffer
     assert (got - want).abs().max().item() <= 2 ** -6 * want.abs().max().item()
     opt.zero_grad()
     assert not opt.flat_grads()[0].any()
