@@ -302,16 +302,14 @@ def compact_adam(master: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.
     bc1 = 1.0 - beta1 ** step
     bc2 = 1.0 - beta2 ** step
     _count()
+    c_dt = dtype_id(compact_out.dtype) if compact_out is not None else _lib.BF16
+    w_dt = dtype_id(w_dtype) if w_dtype is not None else _lib.BF16
     with _timed("compact_adam", master.device, grad.numel()):
-      check(load().smt_compact_adam(
-        ptr(master), ptr(exp_avg), ptr(exp_avg_sq), ptr(grad), dtype_id(grad.dtype), grad.numel(),
-        lr, beta1, beta2, eps, weight_decay, bc1, bc2, grad_scale, ptr(sqnorm), max_norm,
-        ptr(compact_out), dtype_id(compact_out.dtype) if compact_out is not None else BF16_ID,
-        ptr(table), n_blocks, block, dtype_id(w_dtype) if w_dtype is not None else BF16_ID, _st(master)),
-        "smt_compact_adam")
+        check(load().smt_compact_adam(ptr(master), ptr(exp_avg), ptr(exp_avg_sq), ptr(grad), dtype_id(grad.dtype),
+                                      grad.numel(), lr, beta1, beta2, eps, weight_decay, bc1, bc2, grad_scale,
+                                      ptr(sqnorm), max_norm, ptr(compact_out), c_dt, ptr(table), n_blocks, block, w_dt,
+                                      _st(master)), "smt_compact_adam")
 
-
-BF16_ID = _lib.BF16
 
 
 # ---- grouped block-gradient GEMM: several (x, dy) problems in one launch ------------------------------------

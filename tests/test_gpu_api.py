@@ -370,3 +370,34 @@ def test_gradient_accumulation_over_micro_batches(api):
     assert (got - want).abs().max().item() <= 2 ** -6 * want.abs().max().item()
     opt.zero_grad()
     assert not opt.flat_grads()[0].any()
+
+
+def test_smtadam_unflattened_mode_matches_flat_mode(api):
+    """`flatten=False` (a wrapper such as DeepSpeed owns the flat buffers; gradients arrive through autograd) must give
+    the same parameters, masters and dense weights as the native flat arena."""
+    M, _H = api
+    from sparse_matrix_tuning_b200.optim import SMTAdam
+
+    def run(flatten):
+        torch.manual_seed(8)
+        w1 = torch.nn.Parameter(torch.randn(512, 512, device="cuda").bfloat16() * 0.05)
+        w2 = torch.nn.Parameter(torch.randn(256, 512, device="cuda").bfloat16() * 0.05)
+        l1 = M.LinearLayer_MatrixSparsity(w1, index_list=[(0, 1), (1, 1)])
+        l2 = M.LinearLayer_MatrixSparsity(w2, index_list=[(0, 0)])
+        opt = SMTAdam([{"params": [l1.selected_weight, l2.selected_weight], "lr": 2e-3, "weight_decay": 0.01}],
+                      betas=(0.9, 0.95), max_grad_norm=1.0, flatten=flatten)
+        for step in range(3):
+            g = torch.Generator(device="cuda").manual_seed(step)
+            x = torch.randn(2, 32, 512, device="cuda", generator=g).bfloat16()
+            opt.zero_grad()
+            (l2(l1(x)).float().pow(2).mean()).backward()
+            opt.step()
+        masters = [opt.state[p]["master"].reshape(-1).clone() for p in (l1.selected_weight, l2.selected_weight)]
+        return (l1.selected_weight.detach().clone(), l2.selected_weight.detach().clone(), w1.detach().clone(),
+                w2.detach().clone(), masters)
+
+    a, b = run(True), run(False)
+    for t1, t2 in zip(a[:4], b[:4]):
+        assert torch.equal(t1, t2)
+    for m1, m2 in zip(a[4], b[4]):
+        assert torch.equal(m1, m2)

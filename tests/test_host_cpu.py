@@ -197,3 +197,24 @@ def test_no_oracle_import_in_product_package():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
                 assert "/root/reference" not in src, f
+
+
+def test_reference_driver_import_lines_resolve_to_this_package():
+    """with <repo> and <repo>/sparse_matrix_tuning_b200 on PYTHONPATH, the exact import lines of the
+    reference driver (fine_tune.py:39-40) pick up the mirror package."""
+    import subprocess
+    import sys
+    code = (
+        "from smt.smt import convert_linear_layer_to_matrix_sparsity, get_optimizer_sparse_grouped_parameters, "
+        "get_optimizer_qk_augment_grouped_parameters, freeze_unselected_matrix_layer, freeze_unselected_channel_layer, "
+        "convert_linear_layer_to_channel_sparsity\n"
+        "from smt.smt_helper import select_submatrix_based_on_grads, get_blocks, get_named_linears, "
+        "select_channel_based_on_activation\n"
+        "import smt.smt as S\n"
+        "import sparse_matrix_tuning_b200.smt.smt as C, sparse_matrix_tuning_b200.optim\n"
+        "assert S is C and convert_linear_layer_to_matrix_sparsity is C.convert_linear_layer_to_matrix_sparsity\n"
+        "print(S.__file__)\n")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([ROOT, os.path.join(ROOT, "sparse_matrix_tuning_b200")]))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd="/tmp", timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert os.path.join("sparse_matrix_tuning_b200", "smt", "smt.py") in out.stdout
