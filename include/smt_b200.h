@@ -154,6 +154,9 @@ SMT_API size_t smt_block_grad_gemm_grouped_workspace_bytes(int n_items, int bloc
 SMT_API int smt_block_grad_gemm_grouped(const void* maps, const smt_gemm_item* items, int n_items, int64_t T,
                                         int block, int in_dtype, void* out_base, int out_dtype, int accumulate,
                                         void* workspace, size_t workspace_bytes, void* stream);
+/* debug: register a device buffer of 8*max_ctas uint64; each CTA of smt_block_grad_gemm stamps %globaltimer at its
+ * phase boundaries (tools/trace_gemm.py). NULL switches tracing off. Not for production use. */
+SMT_API int smt_debug_set_gemm_trace(void* dev_buf, int max_ctas);
 /* introspection for tests/bench: split-K factor and CTA count the launch above would use. */
 SMT_API int smt_block_grad_gemm_plan(int n_blocks, int block, int64_t T, int in_dtype,
                              int* splits_host, int* ctas_host);

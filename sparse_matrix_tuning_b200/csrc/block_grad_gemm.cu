@@ -34,7 +34,10 @@ namespace {
 
 constexpr int kKTile = 64;                    // tokens per pipeline stage
 constexpr int kChunkBytes = kKTile * 128;     // one {64 features x K_TILE tokens} TMA box of 16-bit data
-constexpr int kEpiWarps = 8;
+#ifndef SMT_GEMM_EPI_WARPS
+#define SMT_GEMM_EPI_WARPS 8                  // multiple of 4 (one TMEM lane quarter per warp % 4)
+#endif
+constexpr int kEpiWarps = SMT_GEMM_EPI_WARPS;
 constexpr int kGemmThreads = 64 + 32 * kEpiWarps;   // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-9 epilogue
 constexpr int kSmemBudget = 200 * 1024;       // pipeline stages (dynamic smem), leaves room for barriers
 constexpr int kMinKTilesPerSplit = 4;
@@ -148,6 +151,17 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define SMT_TRACE(slot)                                                                                   \
+  do {                                                                                                    \
+    if (p.trace != nullptr && (threadIdx.x & 31) == 0)                                                    \
+      p.trace[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 + (slot)] = globaltimer_ns();             \
+  } while (0)
+
 // Shared-memory matrix descriptor, MN-major, SWIZZLE_128B (see header comment for the layout).
 __device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
@@ -173,6 +187,7 @@ struct GemmParams {
   void* out;                      // G base (single problem: block i at i*b*b; grouped: items[i].out_off)
   float* ws;                      // fp32 partial tiles when splits > 1
   int* counters;                  // fused reduction: 2 self-resetting ints per tile (NULL = separate reduce kernel)
+  unsigned long long* trace;      // debug (SMT_GEMM_TRACE=1): 8 globaltimer stamps per CTA, else NULL
   int splits;
   int kt_total;                   // number of K tiles = ceil(T / kKTile)
   int kt_per_split;
@@ -281,6 +296,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) block_grad_umma_kernel(
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x, split = blockIdx.y;
+  if (threadIdx.x == 0) SMT_TRACE(0);                       // CTA start
   const int blk = tile / C::TILES_PER_BLOCK, half = tile % C::TILES_PER_BLOCK;
   const int kt_begin = split * p.kt_per_split;
   const int kt_end = min(kt_begin + p.kt_per_split, p.kt_total);
@@ -323,6 +339,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) block_grad_umma_kernel(
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
   if (threadIdx.x == 0) pdl_launch_dependents();   // the split-K reduce grid may get scheduled (it waits for us)
+  if (threadIdx.x == 0) SMT_TRACE(1);                       // barriers + TMEM ready
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -352,6 +369,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) block_grad_umma_kernel(
         const uint32_t phase = (uint32_t)(it / C::STAGES) & 1u;
         mbar_wait(smem_u32(&full_bar[stage]), phase);
         tc_fence_after();
+        if (it == 0) SMT_TRACE(2);                          // first operands landed
 #pragma unroll
         for (int k = 0; k < kKTile / 16; ++k) {
           // 16 tokens = two 8-row swizzle atoms = 2048 B further down every chunk
@@ -371,10 +389,11 @@ __global__ void __launch_bounds__(kGemmThreads, 1) block_grad_umma_kernel(
     // ===== epilogue: TMEM -> registers -> smem transpose -> coalesced global stores =====
     const int ew = warp - 2;            // 0..7
     const int q = warp & 3;             // TMEM lane quarter this warp may access
-    const int par = ew >> 2;            // two warps per quarter: even / odd column chunks
+    const int par = ew >> 2;            // kEpiWarps / 4 warps per quarter, interleaved over the column chunks
     constexpr int ROWS_PER_MH = B < 128 ? B : 128;
     mbar_wait(smem_u32(&tmem_full_bar), 0);
     tc_fence_after();
+    if (ew == 0) SMT_TRACE(3);                              // accumulators complete
     if (q * 32 < ROWS_PER_MH) {
       // all MMAs have retired => the pipeline buffers are dead; reuse them as transpose staging
       float* stage = reinterpret_cast<float*>(smem_gen) + ew * 32 * kStageRow;
@@ -383,7 +402,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) block_grad_umma_kernel(
 #pragma unroll 1
       for (int mh = 0; mh < MH; ++mh) {
 #pragma unroll 1
-        for (int cc = par; cc < B / 32; cc += 2) {
+        for (int cc = par; cc < B / 32; cc += kEpiWarps / 4) {
           uint32_t r[32];
           tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mh * B + cc * 32), r);
           tmem_ld_wait();
@@ -410,6 +429,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) block_grad_umma_kernel(
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) SMT_TRACE(4);                       // epilogue done
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
@@ -430,6 +450,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) block_grad_umma_kernel(
           __trap();
         }
       }
+      SMT_TRACE(5);                                         // all sibling partials arrived
     }
     __syncthreads();
     const int chunk = ((C::TILE_ELEMS / 8 + p.splits - 1) / p.splits) * 8;
@@ -441,6 +462,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) block_grad_umma_kernel(
     else fused_reduce_slice<SMT_F16>(part0, p.splits, C::TILE_ELEMS, e_begin, e_end, p.out, out_off, p.accumulate != 0);
     __syncthreads();
     if (threadIdx.x == 0) {
+      SMT_TRACE(6);                                         // slice reduced
       if (atomicAdd(arrive + 1, 1) == p.splits - 1) {   // every sibling has passed its wait: safe to re-arm
         arrive[0] = 0;
         arrive[1] = 0;
@@ -717,6 +739,9 @@ int launch_reduce(const float* ws, void* out, const smt_gemm_item* items, int bl
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+unsigned long long* g_trace = nullptr;   // debug only, see smt_debug_set_gemm_trace
+int g_trace_ctas = 0;
+
 size_t plan_workspace_bytes(const Plan& pl) {
   return pl.splits > 1 ? kCounterBytes + (size_t)pl.tiles * pl.splits * pl.tile_elems * sizeof(float) : 0;
 }
@@ -818,6 +843,7 @@ extern "C" SMT_API int smt_block_grad_gemm(const void* x, int64_t ldx, int in_fe
   gp.out = G;
   gp.ws = need > 0 ? reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + kCounterBytes) : nullptr;
   gp.counters = use_fused_reduce(pl) ? reinterpret_cast<int*>(workspace) : nullptr;
+  gp.trace = (g_trace != nullptr && pl.tiles * pl.splits <= g_trace_ctas) ? g_trace : nullptr;
   gp.splits = pl.splits;
   gp.kt_total = pl.kt_total;
   gp.kt_per_split = pl.kt_per_split;
@@ -834,6 +860,15 @@ extern "C" SMT_API int smt_block_grad_gemm(const void* x, int64_t ldx, int in_fe
 }
 
 // ---- grouped entry point: blocks of several (x, dy) problems in one launch ----------------------------------
+
+// Debug facility: when a buffer of 8 * max_ctas uint64 is registered, every CTA of the single-problem GEMM stamps
+// %globaltimer at: 0 start, 1 setup done, 2 first operands landed, 3 accumulators complete, 4 epilogue done,
+// 5 split-K siblings arrived, 6 slice reduced.  Pass NULL to switch it off.
+extern "C" SMT_API int smt_debug_set_gemm_trace(void* dev_buf, int max_ctas) {
+  g_trace = reinterpret_cast<unsigned long long*>(dev_buf);
+  g_trace_ctas = dev_buf ? max_ctas : 0;
+  return SMT_OK;
+}
 
 extern "C" SMT_API int smt_encode_operand_map(void* map_host, const void* base, int64_t features, int64_t T,
                                               int64_t ld, int dtype) {
