@@ -50,6 +50,8 @@ def parse_args():
     ap.add_argument("--no-ckpt", action="store_true", help="disable gradient checkpointing (reference: on, fine_tune.py:192)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seq", type=int, default=512, help="tokens of the bounded CPU sample")
+    ap.add_argument("--attn-ratio", type=float, default=ATTN_RATIO, help="fine_tune.py --downsample_attention_blocks_ratio")
+    ap.add_argument("--mlp-ratio", type=float, default=0.0, help="fine_tune.py --downsample_mlp_blocks_ratio (0 = off)")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra no-checkpointing measurement")
     ap.add_argument("--no-group", action="store_true", help="launch the block-gradient GEMM per module instead of grouped")
     return ap.parse_args()
@@ -236,9 +238,11 @@ def run_ours(args):
                     dims[t] = [p.shape[0], p.shape[1]]
                     break
     total_blocks = sum(p.shape[0] / BLOCK * p.shape[1] / BLOCK for _n, p in named if p.ndim == 2)   # fine_tune.py:231-234
-    n_attn = int(ATTN_RATIO * total_blocks)                       # fine_tune.py:236
-    for name, p in named:                                         # capture needs q/k/v weight gradients only
-        p.requires_grad = ("self_attn" in name) and any(k in name for k in ("q_proj", "k_proj", "v_proj"))
+    n_attn = int(args.attn_ratio * total_blocks)                  # fine_tune.py:236
+    n_mlp = int(args.mlp_ratio * total_blocks)                    # fine_tune.py:239 (0 = MLP not selected, the default)
+    for name, p in named:                                         # capture needs q/k/v (+ MLP) weight gradients only
+        p.requires_grad = (("self_attn" in name) and any(k in name for k in ("q_proj", "k_proj", "v_proj"))) or \
+                          (n_mlp > 0 and "mlp" in name)
     if not args.no_ckpt:
         # non-reentrant checkpointing keeps the whole backward in ONE autograd graph task, so the block-gradient GEMMs
         # of all modules can be deferred to a single grouped launch at the end of the pass
@@ -247,23 +251,34 @@ def run_ours(args):
     model.train()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    acc = WarmupGradAccumulator(block=BLOCK, mode="block_sum")
+    # two accumulators, as the driver keeps `attention_warmup_grads` and `warmup_grads` apart (fine_tune.py:723-765)
+    acc = WarmupGradAccumulator(block=BLOCK, mode="block_sum", mlp=False, attention=True)
+    acc_mlp = WarmupGradAccumulator(block=BLOCK, mode="block_sum", mlp=True, attention=False) if n_mlp > 0 else None
     out = model(input_ids=dev_ids[-1], labels=dev_ids[-1], use_cache=False)
     out.loss.backward()
     acc.accumulate(model.named_parameters())
     dp.allreduce_block_sums(acc)                                  # scores of the DP-mean gradient on every rank
+    if acc_mlp is not None:
+        acc_mlp.accumulate(model.named_parameters())
+        dp.allreduce_block_sums(acc_mlp)
     torch.cuda.synchronize()
     t_capture = time.perf_counter() - t0
     t0 = time.perf_counter()
     keys, scores = acc.scores("mean_abs")
-    sel = H.select_submatrix_from_scores(keys, scores, n_attn, "no_restriction")
+    sel = H.select_submatrix_from_scores(keys, scores, n_attn, "no_restriction")       # fine_tune.py:306-313
+    sel_mlp = {}
+    if acc_mlp is not None:
+        keys_m, scores_m = acc_mlp.scores("mean_abs")
+        sel_mlp = H.select_submatrix_from_scores(keys_m, scores_m, n_mlp, "no_restriction")   # fine_tune.py:319-327
     torch.cuda.synchronize()
     t_select = time.perf_counter() - t0
     dp.assert_same_selection(sel)
+    dp.assert_same_selection(sel_mlp)
     model.zero_grad(set_to_none=True)
-    del acc, out
-    model = M.freeze_unselected_matrix_layer(model, {}, sel)
-    model = M.convert_linear_layer_to_matrix_sparsity(model, {}, sel)
+    del acc, acc_mlp, out
+    model = M.freeze_unselected_matrix_layer(model, sel_mlp, sel)
+    model = M.convert_linear_layer_to_matrix_sparsity(model, sel_mlp, sel)
+    sel = {**sel, **sel_mlp}                                      # below: bookkeeping over every converted module
     groups = M.get_optimizer_sparse_grouped_parameters(model, 0.0, 1e-4)
     opt = SMTAdam(groups, lr=1e-4, betas=(0.9, 0.95), max_grad_norm=1.0)
     n_blocks = sum(len(v) for v in sel.values())
@@ -360,13 +375,15 @@ def run_ours(args):
     n_gemm = len(gemm_t)
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     # minimum HBM bytes of one step's block gradients: every distinct x / dy strip once + the bf16 outputs
-    x_strips = {(k[1], c) for k, idx in sel.items() for _r, c in idx}                 # q/k/v of a layer share x
+    def x_group(kind):                                            # modules that read the same input activation
+        return "attn" if kind in ("q_proj", "k_proj", "v_proj") else ("mlp_in" if kind in ("gate_proj", "up_proj") else kind)
+    x_strips = {(x_group(k[0]), k[1], c) for k, idx in sel.items() for _r, c in idx}
     dy_strips = {(k, r) for k, idx in sel.items() for r, _c in idx}
     gemm_min_bytes = 2.0 * T * BLOCK * (len(x_strips) + len(dy_strips)) + 2.0 * n_blocks * BLOCK * BLOCK
     traffic = None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "r01_bench_gemm_traffic.json")))
-        if args.layers == 32 and not args.no_group and world == 1:
+        if args.layers == 32 and not args.no_group and world == 1 and n_mlp == 0 and args.attn_ratio == ATTN_RATIO:
             traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
     except Exception:
         pass
@@ -387,7 +404,9 @@ def run_ours(args):
     line = {"metric": "tokens/sec/GPU (LLaMA-3-8B SMT 0.71%)", "value": value, "unit": "tokens/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"LLaMA-3-8B SMT 0.71% q/k/v gradient-based selection, bf16, seq {S} x batch {B} per GPU"
+            "config": {"workload": (f"LLaMA-3-8B SMT {100 * (args.attn_ratio + args.mlp_ratio):.2f}% "
+                                    + ("q/k/v" if n_mlp == 0 else "q/k/v + MLP")
+                                    + f" gradient-based selection, bf16, seq {S} x batch {B} per GPU")
                                    + ("" if args.layers == 32 else f" [DEBUG: {args.layers} layers only]"),
                        "selected_blocks": n_blocks, "block": BLOCK, "trainable_elements": trainable,
                        "modules_with_blocks": len(sel), "grouped_block_grad_launch": not args.no_group,
