@@ -157,5 +157,32 @@ class WarmupActivationAccumulator:
             self.acc[key] = torch.zeros(x.shape[1:], dtype=torch.float32, device=x.device)
         ops.act_score_accumulate(self.acc[key], x)
 
+    def attach(self, model, mlp: bool = True, attention: bool = True):
+        """Forward pre-hooks on every targeted nn.Linear of `model` (all of a decoder's Linears in the reference,
+        fine_tune.py:680-689): accumulates sum_b |x| of each module's INPUT.  Keys are (module_name, layer) as in
+        fine_tune.py:659-677 (o_proj is captured too, like the reference's hook)."""
+        self._handles = []
+        for name, mod in model.named_modules():
+            if not isinstance(mod, torch.nn.Linear):
+                continue
+            m = _LAYER_RE.search(name + ".")
+            layer = int(m.group(1)) if m else None
+            key = None
+            if "mlp" in name and mlp:
+                key = ("gate_proj" if "gate_proj" in name else "up_proj" if "up_proj" in name else "down_proj", layer)
+            elif "self_attn" in name and attention:
+                for kind in ("q_proj", "k_proj", "v_proj", "o_proj"):
+                    if kind in name:
+                        key = (kind, layer)
+            if key is None:
+                continue
+            self._handles.append(mod.register_forward_pre_hook(lambda _m, args, key=key: self.add(key, args[0])))
+        return self._handles
+
+    def detach(self) -> None:
+        for h in getattr(self, "_handles", []):
+            h.remove()
+        self._handles = []
+
     def activations(self) -> Dict[Key, torch.Tensor]:
         return dict(self.acc)

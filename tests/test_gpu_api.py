@@ -401,3 +401,67 @@ def test_smtadam_unflattened_mode_matches_flat_mode(api):
         assert torch.equal(t1, t2)
     for m1, m2 in zip(a[4], b[4]):
         assert torch.equal(m1, m2)
+
+
+def test_activation_capture_hooks_and_channel_selection(api):
+    """fine_tune.py:586-708 restated: |x| of every Linear input accumulated over two batches, then
+    select_channel_based_on_activation — device accumulators vs the oracle on the same activations."""
+    _M, H = api
+    from transformers import LlamaConfig, LlamaForCausalLM
+    from sparse_matrix_tuning_b200.warmup import WarmupActivationAccumulator
+    torch.manual_seed(0)
+    cfg = LlamaConfig(vocab_size=512, hidden_size=256, intermediate_size=512, num_hidden_layers=2,
+                      num_attention_heads=4, num_key_value_heads=4, max_position_embeddings=128)
+    model = LlamaForCausalLM(cfg).cuda().bfloat16().eval()
+    ids = [torch.randint(0, 512, (3, 40), generator=torch.Generator().manual_seed(s)).cuda() for s in (1, 2)]
+    ref_acts = {}
+
+    def ref_hook(key):
+        def fn(_m, args):
+            a = args[0].detach().abs().cpu().float()                     # fine_tune.py:651-671
+            ref_acts[key] = a if key not in ref_acts else ref_acts[key] + a
+        return fn
+
+    acc = WarmupActivationAccumulator()
+    acc.attach(model)
+    handles = []
+    for name, mod in model.named_modules():
+        if isinstance(mod, torch.nn.Linear) and ".layers." in name:
+            kind = name.split(".")[-1]
+            handles.append(mod.register_forward_pre_hook(ref_hook((kind, int(name.split(".")[2])))))
+    with torch.no_grad():
+        for b in ids:
+            model(input_ids=b, use_cache=False)
+    acc.detach()
+    for h in handles:
+        h.remove()
+    assert set(acc.activations()) == set(ref_acts) and len(ref_acts) == 2 * 7
+    for k, a in ref_acts.items():
+        assert torch.allclose(acc.activations()[k].cpu(), a.sum(0), rtol=1e-5, atol=1e-5), k
+    for strategy in ("mean_abs", "L2"):
+        want = O.select_channels(ref_acts, 24, "no_restriction", strategy)
+        got = H.select_channel_based_on_activation(acc.activations(), n=24, calculate_strategy=strategy)
+        assert {k: sorted(v) for k, v in got.items()} == {k: sorted(v) for k, v in want.items()}
+
+
+def test_fused_and_separate_split_k_reduction_are_bit_identical(api, monkeypatch):
+    """The in-kernel (cooperative) reduction and the separate reduce kernel sum the same partials in the same order."""
+    from sparse_matrix_tuning_b200 import ops
+    torch.manual_seed(1)
+    for b, T, n in ((256, 4096, 3), (256, 2048, 9), (128, 8192, 5), (64, 4096, 7)):
+        x = torch.randn(T, 1024, device="cuda").bfloat16()
+        dy = torch.randn(T, 1024, device="cuda").bfloat16()
+        perm = torch.randperm((1024 // b) ** 2)[:n]
+        rc = ops.make_block_rc([(int(p) // (1024 // b), int(p) % (1024 // b)) for p in perm], "cuda")
+        assert ops.block_grad_gemm_plan(n, b, T, torch.bfloat16)[0] > 1
+        monkeypatch.delenv("SMT_GEMM_NO_FUSED_REDUCE", raising=False)
+        fused = [ops.block_grad_gemm(x, dy, rc, b, out_dtype=dt) for dt in (torch.float32, torch.bfloat16)]
+        again = ops.block_grad_gemm(x, dy, rc, b, out_dtype=torch.float32)
+        monkeypatch.setenv("SMT_GEMM_NO_FUSED_REDUCE", "1")
+        plain = [ops.block_grad_gemm(x, dy, rc, b, out_dtype=dt) for dt in (torch.float32, torch.bfloat16)]
+        monkeypatch.delenv("SMT_GEMM_NO_FUSED_REDUCE", raising=False)
+        assert torch.equal(fused[0], plain[0]) and torch.equal(fused[1], plain[1]) and torch.equal(fused[0], again)
+    # many back-to-back launches re-arm the arrival counters correctly
+    ref = ops.block_grad_gemm(x, dy, rc, b, out_dtype=torch.float32)
+    for _ in range(50):
+        assert torch.equal(ops.block_grad_gemm(x, dy, rc, b, out_dtype=torch.float32), ref)
