@@ -111,3 +111,19 @@ def test_full_size_scores_and_topk_sorted(ops):
     pairs = list(zip(vals, idx.cpu().tolist()))
     assert pairs == sorted(pairs, reverse=True) and len(set(idx.cpu().tolist())) == 64
     assert min(vals) >= torch.kthvalue(flat.cpu(), flat.numel() - 63).values.item()
+
+
+def test_selection_at_llama_scale_matches_oracle_exactly(ops):
+    """8 LLaMA-3-8B layers of q/k/v accumulators (201 M fp32 elements, 3 072 blocks), n = 217: the drop-in call (host
+    tensors in and device tensors in) returns exactly the oracle's selection — keys, order and (row, col) order."""
+    from oracle import smt_oracle as O
+    from sparse_matrix_tuning_b200.smt import smt_helper as H
+    g = torch.Generator().manual_seed(1234)
+    dims = {"q_proj": [4096, 4096], "k_proj": [1024, 4096], "v_proj": [1024, 4096]}
+    grads = {(m, l): torch.randn(r, c, generator=g) * (1.0 + 0.1 * l) for l in range(8) for m, (r, c) in dims.items()}
+    n = int(0.0071 * 122528 * 8 / 32)
+    want = O.select_submatrix(grads, dims, n)
+    got = H.select_submatrix_based_on_grads(grads, dims, n)
+    assert list(got.items()) == list(want.items())
+    got_dev = H.select_submatrix_based_on_grads({k: v.cuda() for k, v in grads.items()}, dims, n)
+    assert list(got_dev.items()) == list(want.items())
