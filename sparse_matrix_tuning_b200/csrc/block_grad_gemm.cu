@@ -32,7 +32,13 @@
 namespace smt {
 namespace {
 
-constexpr int kKTile = 64;                    // tokens per pipeline stage
+#ifndef SMT_GEMM_KTILE
+#define SMT_GEMM_KTILE 64                     // tokens per pipeline stage (multiple of 16)
+#endif
+#ifndef SMT_GEMM_MAX_STAGES
+#define SMT_GEMM_MAX_STAGES 8
+#endif
+constexpr int kKTile = SMT_GEMM_KTILE;        // tokens per pipeline stage
 constexpr int kChunkBytes = kKTile * 128;     // one {64 features x K_TILE tokens} TMA box of 16-bit data
 #ifndef SMT_GEMM_EPI_WARPS
 #define SMT_GEMM_EPI_WARPS 8                  // multiple of 4 (one TMEM lane quarter per warp % 4)
@@ -40,7 +46,7 @@ constexpr int kChunkBytes = kKTile * 128;     // one {64 features x K_TILE token
 constexpr int kEpiWarps = SMT_GEMM_EPI_WARPS;
 constexpr int kGemmThreads = 64 + 32 * kEpiWarps;   // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-9 epilogue
 constexpr int kSmemBudget = 200 * 1024;       // pipeline stages (dynamic smem), leaves room for barriers
-constexpr int kMinKTilesPerSplit = 4;
+constexpr int kMinKTilesPerSplit = 4 * 64 / kKTile;   // at least 256 tokens per split
 constexpr int kStageRow = 36;                 // floats per row of the epilogue transpose buffer (32 + 4 pad)
 constexpr size_t kCounterBytes = 16384;       // head of the workspace: self-resetting split-K arrival counters
 
@@ -55,7 +61,7 @@ struct Cfg {
   static constexpr int TILE_ELEMS = TILE_ROWS * B;
   static constexpr int STAGE_BYTES = (A_SLOTS + B_LOAD) * kChunkBytes;
   static constexpr int STAGES_RAW = kSmemBudget / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int STAGES = STAGES_RAW > SMT_GEMM_MAX_STAGES ? SMT_GEMM_MAX_STAGES : STAGES_RAW;
   static constexpr int TX_BYTES = (A_LOAD + B_LOAD) * kChunkBytes;
   static constexpr int TMEM_COLS = MH * B < 32 ? 32 : MH * B;  // 512 / 256 / 128 / 64 (powers of two)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + alignment slack
@@ -618,7 +624,7 @@ Plan make_plan(int n_blocks, int block, int64_t T) {
     const int tiles = n_blocks * tpb;
     const int tile_rows = block >= 128 ? 128 * mh : block;
     const double tile_bytes = 4.0 * tile_rows * block;                 // fp32 tile
-    const double c_kt = block == 256 ? (mh == 2 ? 0.64 : 0.41) : 0.30;
+    const double c_kt = (block == 256 ? (mh == 2 ? 0.64 : 0.41) : 0.30) * kKTile / 64.0;   // fitted per 64 tokens
     int max_splits = kt_total / kMinKTilesPerSplit;
     if (max_splits < 1) max_splits = 1;
     if (max_splits > 64) max_splits = 64;
