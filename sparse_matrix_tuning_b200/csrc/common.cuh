@@ -109,15 +109,6 @@ __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
 }
 
 template <int DT>
-struct elem_t;
-template <>
-struct elem_t<SMT_F32> { using type = float; };
-template <>
-struct elem_t<SMT_BF16> { using type = __nv_bfloat16; };
-template <>
-struct elem_t<SMT_F16> { using type = __half; };
-
-template <int DT>
 __device__ __forceinline__ float load_as_float(const void* p, int64_t i) {
   if (DT == SMT_F32) return reinterpret_cast<const float*>(p)[i];
   if (DT == SMT_BF16) return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(p)[i]);

@@ -18,7 +18,7 @@ on CPU with the gloo backend in tests/test_dp_gloo.py.
 from __future__ import annotations
 
 import hashlib
-from typing import Iterable, List, Optional
+from typing import Iterable
 
 import torch
 import torch.distributed as dist

@@ -30,7 +30,7 @@ from __future__ import annotations
 import re
 import threading
 import weakref
-from typing import Dict, List, Sequence, Tuple
+from typing import Dict, Tuple
 
 import torch
 from torch import nn

@@ -3,7 +3,6 @@ gradient all-reduce with the mean folded into grad_scale, the block-sum all-redu
 import os
 import socket
 
-import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp

@@ -9,7 +9,6 @@ import torch
 
 from oracle import smt_oracle as O
 from sparse_matrix_tuning_b200 import ops
-from sparse_matrix_tuning_b200.smt import smt as M
 
 flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
 
