@@ -171,9 +171,11 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": "tokens/sec/GPU (LLaMA-3-8B SMT 0.71%)", "value": tps, "unit": "tokens/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms * LLAMA3_8B["num_hidden_layers"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "LLaMA-3-8B SMT 0.71% q/k/v (869 blocks of 256x256), bf16, seq 512, CPU bounded sample",
-                       "note": "the reference is pure Python/PyTorch and is not present on the GPU box; this arm runs the "
-                               "oracle port of its hot path (oracle/smt_oracle.py) on the host cores"},
+            "config": {"workload": f"LLaMA-3-8B SMT 0.71% q/k/v gradient-based selection, bf16, seq {args.seq} x batch "
+                                   f"{args.batch} per GPU",
+                       "note": "same workload as the GPU arm, measured on a bounded sample (see cpu_baseline.sample); the "
+                               "reference is pure Python/PyTorch and is not present on the GPU box, so this arm runs the "
+                               "oracle port of its hot path (oracle/smt_oracle.py) on all host cores"},
             "cpu_baseline": {"value": tps, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": tps, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}

@@ -19,10 +19,12 @@
 // issuer / TMEM owner, 8 epilogue warps.  For b = 256 a tile is either the whole block (MH = 2: two M=128
 // accumulators share one x strip, N = 256, all 512 TMEM columns, 256 flop per byte of shared-memory fill)
 // or half a block (MH = 1: used when there are few blocks, it halves the split-K partial traffic).  With few
-// tiles per launch the token range is split across CTAs; partial tiles go to an fp32 workspace and a second
-// kernel (launched with programmatic dependent launch, so its launch latency overlaps the GEMM) sums them in
-// a fixed order: deterministic, no atomics.  The epilogue transposes 32x32 accumulator sub-tiles through
-// shared memory so that every global store instruction writes whole 128-byte rows.
+// tiles per launch the token range is split across CTAs and partial tiles go to an fp32 workspace.  When the
+// grid fits in one wave the kernel is launched cooperatively and the reduction is fused: after a per-tile
+// arrival counter, each sibling CTA sums its slice of the tile over all partials in the fixed order 0..splits-1.
+// Larger grids use a second kernel (programmatic dependent launch hides its launch latency).  Either way the
+// sum order is fixed: deterministic, no atomics on data.  The epilogue transposes 32x32 accumulator sub-tiles
+// through shared memory so that every global store instruction writes whole 128-byte rows.
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
