@@ -146,6 +146,44 @@ def gen_config1(S, H):
     print("config1:", dict(sel), "losses", losses, "norms", grad_norms)
 
 
+def gen_config1_bf16(S):
+    """Same model / batches as config 1 but in bf16 (the dtype the reference trains in, fine_tune.py --dtype bf16):
+    the SMT steady state only — selection is TAKEN from the fp32 golden (bf16 noise could flip near-ties between
+    two implementations, which would make a cross-implementation comparison of everything downstream meaningless).
+    Stores losses, first-step gradients and the clipped-AdamW-updated compact weights after 4 steps.  The optimizer
+    runs on fp32 masters of the bf16 compact parameters, as DeepSpeed's bf16 engine does (fine_tune.py:379-384)."""
+    gold = torch.load(os.path.join(OUT, "config1_e2e.pt"), weights_only=False)
+    sel = {k: [tuple(t) for t in v] for k, v in gold["selection"]}
+    model, batches = GI.make_config1()
+    model = model.to(torch.bfloat16)
+    model = S.freeze_unselected_matrix_layer(model, {}, sel)
+    model = S.convert_linear_layer_to_matrix_sparsity(model, {}, sel)
+    named = [(n, p) for n, p in model.named_parameters() if p.requires_grad]
+    masters = [p.detach().float().clone().requires_grad_(True) for _n, p in named]
+    opt = torch.optim.AdamW(masters, lr=GI.CONFIG1["smt_lr"], betas=(0.9, 0.95), eps=1e-8, weight_decay=0.0)
+    losses, first_grads = [], None
+    for it in range(GI.CONFIG1["sparse_steps"]):
+        for _n, p in named:
+            p.grad = None
+        b = batches[GI.CONFIG1["warmup_steps"] + it]
+        out = model(input_ids=b, labels=b, use_cache=False)
+        out.loss.backward()
+        if first_grads is None:
+            first_grads = {n: p.grad.detach().clone() for n, p in named}
+        for m, (_n, p) in zip(masters, named):
+            m.grad = p.grad.detach().float()
+        torch.nn.utils.clip_grad_norm_(masters, 1.0)
+        opt.step()
+        with torch.no_grad():
+            for m, (_n, p) in zip(masters, named):
+                p.copy_(m.to(torch.bfloat16))
+        losses.append(out.loss.item())
+    torch.save({"selection": gold["selection"], "losses": losses, "first_grads": first_grads,
+                "final_selected": {n: p.detach().clone() for n, p in named}},
+               os.path.join(OUT, "config1_bf16.pt"))
+    print("config1 bf16 losses", losses)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     S, H = load_reference()
@@ -154,6 +192,7 @@ def main():
     gen_channels(H)
     gen_linearz(S)
     gen_config1(S, H)
+    gen_config1_bf16(S)
 
 
 if __name__ == "__main__":

@@ -465,3 +465,45 @@ def test_fused_and_separate_split_k_reduction_are_bit_identical(api, monkeypatch
     ref = ops.block_grad_gemm(x, dy, rc, b, out_dtype=torch.float32)
     for _ in range(50):
         assert torch.equal(ops.block_grad_gemm(x, dy, rc, b, out_dtype=torch.float32), ref)
+
+
+def test_config1_bf16_steady_state_vs_reference_golden(api):
+    """BASELINE config 1 in bf16 (the training dtype): the reference's own bf16 SMT steps (CPU, fp32-master AdamW with
+    clip 1.0) against SMTAdam + the tcgen05 block-gradient GEMM, with the reference's selection.
+    Tolerances: losses 2e-2 abs (bf16 forward of a 32 000-way softmax on two different back ends), first-step block
+    gradients 2^-6 of the tensor max, final compact weights within a few bf16 ulps of 0.02-scale weights."""
+    M, _H = api
+    from sparse_matrix_tuning_b200.optim import SMTAdam
+    gold = load_golden("config1_bf16.pt")
+    c = GI.CONFIG1
+    sel = {k: [tuple(t) for t in v] for k, v in gold["selection"]}
+    model, batches = GI.make_config1()
+    model = model.to(torch.bfloat16).cuda()
+    batches = [b.cuda() for b in batches]
+    model = M.freeze_unselected_matrix_layer(model, {}, sel)
+    model = M.convert_linear_layer_to_matrix_sparsity(model, {}, sel)
+    opt = SMTAdam(M.get_optimizer_sparse_grouped_parameters(model, 0.0, c["smt_lr"]), lr=c["smt_lr"], betas=(0.9, 0.95),
+                  max_grad_norm=1.0)
+    M.set_grouped_backward(True)
+    try:
+        losses = []
+        for it in range(c["sparse_steps"]):
+            opt.zero_grad()
+            b = batches[c["warmup_steps"] + it]
+            out = model(input_ids=b, labels=b, use_cache=False)
+            out.loss.backward()
+            if it == 0:
+                for n, p in model.named_parameters():
+                    if p.requires_grad:
+                        ref = gold["first_grads"][n].float()
+                        assert (p.grad.float().cpu() - ref).abs().max().item() <= 2 ** -6 * ref.abs().max().item(), n
+            opt.step()
+            losses.append(out.loss.item())
+    finally:
+        M.set_grouped_backward(False)
+    assert max(abs(a - b) for a, b in zip(losses, gold["losses"])) <= 2e-2, (losses, gold["losses"])
+    for n, p in model.named_parameters():
+        if p.requires_grad:
+            d = (p.detach().float().cpu() - gold["final_selected"][n].float()).abs()
+            assert d.max().item() <= 2 * c["sparse_steps"] * c["smt_lr"] + 2 ** -8 * 0.1, (n, d.max().item())
+            assert d.mean().item() <= 2e-5, (n, d.mean().item())
