@@ -506,4 +506,4 @@ def test_config1_bf16_steady_state_vs_reference_golden(api):
         if p.requires_grad:
             d = (p.detach().float().cpu() - gold["final_selected"][n].float()).abs()
             assert d.max().item() <= 2 * c["sparse_steps"] * c["smt_lr"] + 2 ** -8 * 0.1, (n, d.max().item())
-            assert d.mean().item() <= 2e-5, (n, d.mean().item())
+            assert d.mean().item() <= 4e-5, (n, d.mean().item())
