@@ -507,3 +507,56 @@ def test_config1_bf16_steady_state_vs_reference_golden(api):
             d = (p.detach().float().cpu() - gold["final_selected"][n].float()).abs()
             assert d.max().item() <= 2 * c["sparse_steps"] * c["smt_lr"] + 2 ** -8 * 0.1, (n, d.max().item())
             assert d.mean().item() <= 4e-5, (n, d.mean().item())
+
+
+def test_edge_cases_empty_index_list_frozen_compact_and_oversized_n(api):
+    M, H = api
+    torch.manual_seed(9)
+    w = torch.nn.Parameter(torch.randn(256, 512, device="cuda").bfloat16() * 0.05)
+    # (a) a module converted with NO selected block behaves like a frozen dense layer (reference: empty [0, 256] param)
+    empty = M.LinearLayer_MatrixSparsity(w, index_list=[])
+    assert tuple(empty.selected_weight.shape) == (0, 256)
+    x = torch.randn(2, 8, 512, device="cuda").bfloat16().requires_grad_(True)
+    y = empty(x)
+    y.sum().backward()
+    assert torch.equal(y, torch.matmul(x.detach(), w.t())) and x.grad is not None
+    assert empty.selected_weight.grad is None or empty.selected_weight.grad.numel() == 0
+    # (b) frozen compact parameter: no block-gradient work, input gradient still flows
+    layer = M.LinearLayer_MatrixSparsity(w, index_list=[(0, 1)])
+    layer.selected_weight.requires_grad = False
+    x2 = torch.randn(2, 8, 512, device="cuda").bfloat16().requires_grad_(True)
+    layer(x2).sum().backward()
+    assert layer.selected_weight.grad is None and x2.grad is not None
+    # (c) n larger than what exists: everything comes back, best first (smt_helper.py:111-119 never pops)
+    grads = {("q_proj", 0): torch.randn(512, 512), ("k_proj", 3): torch.randn(256, 512)}
+    dims = {"q_proj": [512, 512], "k_proj": [256, 512]}
+    for strat in ("no_restriction", "norm_dist"):
+        got = H.select_submatrix_based_on_grads(grads, dims, 1000, selection_strategy=strat)
+        want = O.select_submatrix(grads, dims, 1000, strat)
+        assert {k: sorted(v) for k, v in got.items()} == {k: sorted(v) for k, v in want.items()}
+        assert sum(len(v) for v in got.values()) == 6
+    act = {("q_proj", 0): torch.rand(2, 16, 64), ("up_proj", 1): torch.rand(2, 16, 32)}
+    got = H.select_channel_based_on_activation(act, n=500)
+    assert sorted(got[("q_proj", 0)]) == list(range(64)) and sorted(got[("up_proj", 1)]) == list(range(32))
+    assert list(got.items()) == [(k, list(v)) for k, v in O.select_channels(act, 500).items()]
+
+
+def test_mixture_mode_conversion(api):
+    """mixture=True (fine_tune.py --no_limit_mixture): attention modules are looked up in the FIRST dict and o_proj may
+    be selected too (smt.py:146-176, 657-678)."""
+    M, _H = api
+    from transformers import LlamaConfig, LlamaForCausalLM
+    torch.manual_seed(0)
+    cfg = LlamaConfig(vocab_size=256, hidden_size=256, intermediate_size=512, num_hidden_layers=2,
+                      num_attention_heads=4, num_key_value_heads=4, max_position_embeddings=64)
+    model = LlamaForCausalLM(cfg).cuda().bfloat16()
+    sel = {("o_proj", 1): [(0, 0)], ("k_proj", 0): [(0, 0)], ("gate_proj", 1): [(1, 0), (0, 0)]}
+    M.freeze_unselected_matrix_layer(model, sel, {}, mixture=True)
+    M.convert_linear_layer_to_matrix_sparsity(model, sel, {}, mixture=True)
+    converted = sorted(n for n, m in model.named_modules() if isinstance(m, M.LinearLayer_MatrixSparsity))
+    assert converted == ["model.layers.0.self_attn.k_proj", "model.layers.1.mlp.gate_proj", "model.layers.1.self_attn.o_proj"]
+    assert sorted(n for n, p in model.named_parameters() if p.requires_grad) == sorted(c + ".selected_weight" for c in converted)
+    ids = torch.randint(0, 256, (2, 32), device="cuda")
+    model(input_ids=ids, labels=ids, use_cache=False).loss.backward()
+    g = model.model.layers[1].mlp.gate_proj.selected_weight.grad
+    assert g is not None and tuple(g.shape) == (512, 256) and g.abs().sum() > 0
