@@ -4,7 +4,7 @@ next to this repo's kernels, on the same tensors.  Measurement tooling only (imp
 import os
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch
 
 from oracle import smt_oracle as O
