@@ -140,7 +140,10 @@ SMT_API int smt_block_grad_gemm(const void* x, int64_t ldx, int in_features,
  * smt_encode_operand_map (one per distinct x or dy operand, all with the same T and dtype); `items` is a device
  * array with one entry per block: which dy / x descriptor, which block (row, col), and where its b x b result goes
  * (`out_off` = element offset from `out_base`, a multiple of 8).  Same arithmetic and determinism as the
- * single-problem call. */
+ * single-problem call.
+ * Row-sharing pairs: the first `n_paired` items (an even number, 0 = none) must come as consecutive pairs that have
+ * the same `map_dy` and the same `row`.  When the launch is large enough to need no split-K (b = 256), those pairs run
+ * as 2-CTA clusters that fetch the shared dy strip once and TMA-multicast it to both CTAs. */
 typedef struct smt_gemm_item {
   uint32_t map_dy;   /* index into maps: descriptor of the dy operand   */
   uint32_t map_x;    /* index into maps: descriptor of the x operand    */
@@ -150,10 +153,10 @@ typedef struct smt_gemm_item {
 } smt_gemm_item;
 SMT_API int smt_encode_operand_map(void* map_host, const void* base, int64_t features, int64_t T, int64_t ld,
                                    int dtype);
-SMT_API size_t smt_block_grad_gemm_grouped_workspace_bytes(int n_items, int block, int64_t T);
-SMT_API int smt_block_grad_gemm_grouped(const void* maps, const smt_gemm_item* items, int n_items, int64_t T,
-                                        int block, int in_dtype, void* out_base, int out_dtype, int accumulate,
-                                        void* workspace, size_t workspace_bytes, void* stream);
+SMT_API size_t smt_block_grad_gemm_grouped_workspace_bytes(int n_items, int n_paired, int block, int64_t T);
+SMT_API int smt_block_grad_gemm_grouped(const void* maps, const smt_gemm_item* items, int n_items, int n_paired,
+                                        int64_t T, int block, int in_dtype, void* out_base, int out_dtype,
+                                        int accumulate, void* workspace, size_t workspace_bytes, void* stream);
 /* debug: register a device buffer of 8*max_ctas uint64; each CTA of smt_block_grad_gemm stamps %globaltimer at its
  * phase boundaries (tools/trace_gemm.py). NULL switches tracing off. Not for production use. */
 SMT_API int smt_debug_set_gemm_trace(void* dev_buf, int max_ctas);

@@ -363,14 +363,25 @@ class BlockGradBatch:
 
         esize = prs[0][3].element_size()
         base_ptr = min(pr[3].data_ptr() for pr in prs)
-        items = []
+        entries = []
         for x2d, dy2d, idx, out, _b in prs:
             mx, mdy = map_index(x2d), map_index(dy2d)
             off0 = (out.data_ptr() - base_ptr) // esize
             # CTAs are scheduled in item order: keep blocks that share a dy strip (same block row) adjacent so that
             # they run in the same wave and hit each other's lines in L2
             for i, (r, c) in sorted(enumerate(idx), key=lambda t: (t[1][0], t[1][1])):
-                items.append((mdy, mx, r, c, off0 + i * block * block))
+                entries.append((mdy, mx, r, c, off0 + i * block * block))
+        # consecutive blocks of the same block row of the same dy operand form a pair: the kernel runs pairs as
+        # 2-CTA clusters that fetch the shared dy strip once (TMA multicast); the rest are singles
+        pairs, singles, i = [], [], 0
+        while i < len(entries):
+            if i + 1 < len(entries) and entries[i][0] == entries[i + 1][0] and entries[i][2] == entries[i + 1][2]:
+                pairs += [entries[i], entries[i + 1]]
+                i += 2
+            else:
+                singles.append(entries[i])
+                i += 1
+        items, n_paired = pairs + singles, len(pairs)
         n_items, n_maps = len(items), len(maps)
         item_dt = np.dtype([("map_dy", "<u4"), ("map_x", "<u4"), ("row", "<i4"), ("col", "<i4"), ("out_off", "<i8")])
         nbytes = n_maps * 128 + n_items * item_dt.itemsize
@@ -382,10 +393,10 @@ class BlockGradBatch:
                   "smt_encode_operand_map")
         host[n_maps * 128:].view(item_dt)[:] = np.array(items, dtype=item_dt)
         dev_buf = stage.to(dev, non_blocking=True)
-        ws_bytes = lib.smt_block_grad_gemm_grouped_workspace_bytes(n_items, block, T)
+        ws_bytes = lib.smt_block_grad_gemm_grouped_workspace_bytes(n_items, n_paired, block, T)
         ws = _workspace(ws_bytes, dev)
         with _timed("block_grad_gemm", dev, (n_items, block, T)):
-            check(lib.smt_block_grad_gemm_grouped(dev_buf.data_ptr(), dev_buf.data_ptr() + n_maps * 128, n_items, T, block,
-                                                  in_id, base_ptr, dtype_id(out_dt), 1 if accumulate else 0, ptr(ws),
-                                                  ws_bytes, stream_ptr(dev)), "smt_block_grad_gemm_grouped")
+            check(lib.smt_block_grad_gemm_grouped(dev_buf.data_ptr(), dev_buf.data_ptr() + n_maps * 128, n_items, n_paired,
+                                                  T, block, in_id, base_ptr, dtype_id(out_dt), 1 if accumulate else 0,
+                                                  ptr(ws), ws_bytes, stream_ptr(dev)), "smt_block_grad_gemm_grouped")
         _count(lib.smt_last_launch_count())
