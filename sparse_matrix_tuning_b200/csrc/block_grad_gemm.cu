@@ -959,10 +959,12 @@ extern "C" SMT_API int smt_encode_operand_map(void* map_host, const void* base, 
 }
 
 namespace {
-// Row-sharing pairs (the first n_paired items) take the 2-CTA multicast kernel when the launch is big enough to need
-// no split-K (whole-block tiles); otherwise pairing is ignored and every item goes through the planner as a single.
+// Row-sharing pairs (the first n_paired items) can take the 2-CTA multicast kernel when the launch is big enough to
+// need no split-K (whole-block tiles).  OPT-IN (SMT_GEMM_PAIRS=1): measured on B200 the multicast saves no time -- the
+// main loop is bound by the per-SM shared-memory fill, which multicast does not reduce -- and the second launch costs
+// ~85 us in bench.py (profiles/r01_kernels.md, "multicast pairs").  By default every item goes through the planner.
 bool use_pairs(int n_items, int n_paired, int block, int64_t T) {
-  if (block != 256 || n_paired < 2 || (n_paired & 1) || n_paired > n_items || env_int("SMT_GEMM_NO_PAIRS", 0)) return false;
+  if (block != 256 || n_paired < 2 || (n_paired & 1) || n_paired > n_items || !env_int("SMT_GEMM_PAIRS", 0)) return false;
   const Plan pl = make_plan(n_items, block, T);
   return pl.splits == 1 && pl.mh == 2;
 }

@@ -371,8 +371,8 @@ class BlockGradBatch:
             # they run in the same wave and hit each other's lines in L2
             for i, (r, c) in sorted(enumerate(idx), key=lambda t: (t[1][0], t[1][1])):
                 entries.append((mdy, mx, r, c, off0 + i * block * block))
-        # consecutive blocks of the same block row of the same dy operand form a pair: the kernel runs pairs as
-        # 2-CTA clusters that fetch the shared dy strip once (TMA multicast); the rest are singles
+        # consecutive blocks of the same block row of the same dy operand form a pair and are placed first: adjacent
+        # tiles then share their dy strip through L2 (and, with SMT_GEMM_PAIRS=1, run as 2-CTA multicast clusters)
         pairs, singles, i = [], [], 0
         while i < len(entries):
             if i + 1 < len(entries) and entries[i][0] == entries[i + 1][0] and entries[i][2] == entries[i + 1][2]:
