@@ -117,6 +117,22 @@ SMT_API int smt_block_gather(const smt_block_ref* table, int n_blocks, int block
 SMT_API int smt_block_scatter(const smt_block_ref* table, int n_blocks, int block, int elem_bytes,
                       const void* compact, void* stream);
 
+/* ---- channel (input-column) movement for the channel-sparsity layer -------------------- */
+
+/* out[t, i] <- x[t, idx[i]], t in [0, T), i in [0, n): the packed copy of the selected input channels that
+ * linearChannel.forward saves for backward (smt.py:240-247, n strided slice copies there).  `ldx` in elements. */
+SMT_API int smt_channel_gather(const void* x, int64_t T, int64_t ldx, const int32_t* idx, int n, int elem_bytes,
+                       void* out, void* stream);
+/* compact[i, o] <- W[o, idx[i]]  (LinearLayer_ChannelSparsity.__init__, smt.py:198-200) and
+ * W[o, idx[i]] <- compact[i, o]  (its forward, smt.py:208-211), o in [0, out_features).  The reference copies weight
+ * ROW idx[i] although idx are input channels and its gradient (smt.py:283-284) is that of weight COLUMN idx[i]; the
+ * column form here is the consistent one (identical gradient formula, works for non-square weights).
+ * `compact` is a contiguous [n, out_features] array; idx must not repeat for the scatter. */
+SMT_API int smt_column_gather(const void* W, int64_t ldw, int out_features, int in_features, const int32_t* idx,
+                      int n, int elem_bytes, void* compact, void* stream);
+SMT_API int smt_column_scatter(void* W, int64_t ldw, int out_features, int in_features, const int32_t* idx, int n,
+                       int elem_bytes, const void* compact, void* stream);
+
 /* ---- block-gradient contraction (linearZ.backward, smt.py:386-404) -------------------- */
 
 /* G[i*b + o, k] (+)= sum_t dy[t, row_i*b + o] * x[t, col_i*b + k],  t in [0, T).

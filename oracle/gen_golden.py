@@ -83,6 +83,22 @@ def gen_linearz(S):
     print(f"linearZ: {len(cases)} cases")
 
 
+def gen_linearchannel(S):
+    """The reference's channel layer on square weights: y, grad_input and the [n, out] channel gradient."""
+    cases = []
+    for spec in GI.LINEARCHANNEL_SPECS:
+        x, dy, w, index_list = GI.make_linearchannel_inputs(spec)
+        layer = S.LinearLayer_ChannelSparsity(torch.nn.Parameter(w.clone()), bias=None, index_list=index_list)
+        xin = x.clone().requires_grad_(True)
+        y = layer(xin)
+        y.backward(dy)
+        cases.append({"spec": spec, "x": x, "dy": dy, "w": w, "index_list": index_list,
+                      "y": y.detach().clone(), "grad_weight": layer.selected_weight.grad.detach().clone(),
+                      "grad_input": xin.grad.detach().clone()})
+    torch.save(cases, os.path.join(OUT, "linearchannel_cases.pt"))
+    print(f"linearChannel: {len(cases)} cases")
+
+
 def gen_config1(S, H):
     """BASELINE config 1: 2-layer random-init LLaMA (hidden 512), 256x256 blocks, 1 % q/k/v, fp32 CPU.
     Flow (restating fine_tune.py): budget :231-239, two warm-up backward passes captured as :716-768 (no
@@ -191,6 +207,7 @@ def main():
     gen_selection(H)
     gen_channels(H)
     gen_linearz(S)
+    gen_linearchannel(S)
     gen_config1(S, H)
     gen_config1_bf16(S)
 

@@ -110,6 +110,27 @@ LINEARZ_SPECS = [
 ]
 
 
+# linearChannel (smt.py:220-296) runs in the reference only for SQUARE weights (it copies weight rows into an
+# [n, in_features] parameter but produces an [n, out_features] gradient)
+LINEARCHANNEL_SPECS = [
+    {"name": "fp32_sq", "dtype": "float32", "B": 2, "S": 24, "in": 256, "out": 256,
+     "index_list": [200, 3, 77, 78, 255, 0], "seed": 51},
+    {"name": "bf16_sq_B4", "dtype": "bfloat16", "B": 4, "S": 40, "in": 512, "out": 512,
+     "index_list": [511, 17, 300, 301, 302, 5, 64, 128, 256, 9, 100], "seed": 52},
+    {"name": "bf16_sq_B1", "dtype": "bfloat16", "B": 1, "S": 96, "in": 384, "out": 384,
+     "index_list": [1], "seed": 53},
+]
+
+
+def make_linearchannel_inputs(spec):
+    g = torch.Generator().manual_seed(spec["seed"])
+    dt = getattr(torch, spec["dtype"])
+    x = torch.randn(spec["B"], spec["S"], spec["in"], generator=g).to(dt)
+    dy = torch.randn(spec["B"], spec["S"], spec["out"], generator=g).to(dt)
+    w = (torch.randn(spec["out"], spec["in"], generator=g) * 0.02).to(dt)
+    return x, dy, w, [int(i) for i in spec["index_list"]]
+
+
 def make_linearz_inputs(spec):
     g = torch.Generator().manual_seed(spec["seed"])
     dt = getattr(torch, spec["dtype"])

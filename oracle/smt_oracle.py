@@ -230,6 +230,31 @@ def linearz_backward(x: torch.Tensor, dy: torch.Tensor, weight: torch.Tensor, in
     return gi, gw
 
 
+def linearchannel_backward(x: torch.Tensor, dy: torch.Tensor, weight: torch.Tensor, channel_index_list):
+    """linearChannel.forward/backward, smt.py:240-247, 283-286.  x: [B,S,in], dy: [B,S,out].  Returns
+    (grad_input, grad_weight [n, out]): one batched matmul in the input dtype, then a sum over the batch."""
+    partial = torch.empty(x.shape[0], x.shape[1], len(channel_index_list), dtype=x.dtype)
+    for i, index in enumerate(channel_index_list):
+        partial[:, :, i] = x[:, :, index]                                       # smt.py:245-247
+    gw = torch.sum(torch.matmul(partial.permute(0, 2, 1), dy), dim=0)           # smt.py:283-284
+    gi = torch.matmul(dy, weight)                                               # smt.py:286
+    return gi, gw
+
+
+def gather_columns(weight: torch.Tensor, channel_index_list) -> torch.Tensor:
+    """Column form of smt.py:198-200 (the reference copies ROWS there — inconsistent with its own gradient, see
+    DESIGN.md section 6b): compact[i, :] = W[:, idx[i]]."""
+    return torch.stack([weight[:, int(i)] for i in channel_index_list]) if len(channel_index_list) else \
+        torch.empty(0, weight.shape[0], dtype=weight.dtype)
+
+
+def scatter_columns(weight: torch.Tensor, selected: torch.Tensor, channel_index_list) -> torch.Tensor:
+    """Column form of smt.py:208-211: W[:, idx[i]] = compact[i, :] (in place)."""
+    for i, index in enumerate(channel_index_list):
+        weight[:, int(index)] = selected[i, :]
+    return weight
+
+
 def block_grad_truth(x: torch.Tensor, dy: torch.Tensor, index_list, block: int = BLOCK) -> torch.Tensor:
     """fp64 value of the same contraction (the quantity both the reference and the kernel approximate)."""
     x2 = x.reshape(-1, x.shape[-1]).double()

@@ -52,6 +52,9 @@ _SIGNATURES = {
     "smt_topk_blocks": (C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P, C.c_int, _P, _P, C.c_size_t, _P]),
     "smt_block_gather": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "smt_block_scatter": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, _P, _P]),
+    "smt_channel_gather": (C.c_int, [_P, C.c_int64, C.c_int64, _P, C.c_int, C.c_int, _P, _P]),
+    "smt_column_gather": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, _P]),
+    "smt_column_scatter": (C.c_int, [_P, C.c_int64, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, _P]),
     "smt_block_grad_gemm_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int64, C.c_int]),
     "smt_block_grad_gemm": (C.c_int, [_P, C.c_int64, C.c_int, _P, C.c_int64, C.c_int, C.c_int64, C.c_int,
                                       _P, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, C.c_size_t, _P]),
@@ -113,10 +116,19 @@ def stream_ptr(device=None) -> int:
 
 
 def require_cuda(*tensors: torch.Tensor) -> None:
+    current = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise SMTLibraryError("SMT kernels need CUDA tensors; there is no CPU path "
                                   f"(got a tensor on {t.device})")
+        if current is None:
+            current = torch.cuda.current_device()
+        if t.device.index != current:
+            # the library launches on the calling thread's current device (one process per GPU)
+            raise SMTLibraryError(f"tensor on {t.device} but the current CUDA device is cuda:{current}; "
+                                  "call torch.cuda.set_device / use torch.cuda.device(...) around the op")
 
 
 def ptr(t) -> int:

@@ -22,8 +22,17 @@ import torch
 from .smt import smt as _smt
 
 
-def sparse_modules(model) -> "OrderedDict[str, _smt.LinearLayer_MatrixSparsity]":
-    return OrderedDict((n, m) for n, m in model.named_modules() if isinstance(m, _smt.LinearLayer_MatrixSparsity))
+_SPARSE_TYPES = (_smt.LinearLayer_MatrixSparsity, _smt.LinearLayer_ChannelSparsity)
+
+
+def sparse_modules(model) -> "OrderedDict[str, torch.nn.Module]":
+    """Every converted module (block- or channel-sparse), by qualified name."""
+    return OrderedDict((n, m) for n, m in model.named_modules() if isinstance(m, _SPARSE_TYPES))
+
+
+def _plain_index(entry):
+    """(row, col) block index -> tuple of ints; channel index -> int."""
+    return tuple(map(int, entry)) if isinstance(entry, (tuple, list)) else int(entry)
 
 
 def merged_state_dict(model) -> "OrderedDict[str, torch.Tensor]":
@@ -41,8 +50,8 @@ def merged_state_dict(model) -> "OrderedDict[str, torch.Tensor]":
 def smt_state(model, optimizer: Optional[torch.optim.Optimizer] = None) -> Dict:
     mods = sparse_modules(model)
     state = {"format": 1,
-             "block": {n: m.block for n, m in mods.items()},
-             "index_lists": {n: [tuple(map(int, rc)) for rc in m.index_list] for n, m in mods.items()},
+             "block": {n: getattr(m, "block", None) for n, m in mods.items()},      # None = channel-sparse module
+             "index_lists": {n: [_plain_index(e) for e in m.index_list] for n, m in mods.items()},
              "selected_weight": {n: m.selected_weight.detach().clone() for n, m in mods.items()}}
     if optimizer is not None:
         state["optimizer"] = optimizer.state_dict()
@@ -68,7 +77,7 @@ def load_smt_state(model, state: Dict, optimizer: Optional[torch.optim.Optimizer
         raise ValueError("converted modules do not match the checkpoint: "
                          f"{sorted(set(mods) ^ set(state['index_lists']))}")
     for name, mod in mods.items():
-        if [tuple(map(int, rc)) for rc in mod.index_list] != [tuple(rc) for rc in state["index_lists"][name]]:
+        if [_plain_index(e) for e in mod.index_list] != [_plain_index(e) for e in state["index_lists"][name]]:
             raise ValueError(f"index list of {name} differs from the checkpoint (order defines the row layout)")
         with torch.no_grad():
             mod.selected_weight.copy_(state["selected_weight"][name].to(mod.selected_weight.device))

@@ -20,6 +20,12 @@ LAUNCHES = {"total": 0}
 _timers: dict = {}
 
 
+def _req(cond: bool, what: str) -> None:
+    """Argument validation that survives `python -O` (unlike assert): the C-ABI trusts these shapes."""
+    if not cond:
+        raise _lib.SMTLibraryError(f"invalid argument: expected {what}")
+
+
 def _count(n: int = 1) -> None:
     LAUNCHES["total"] += n
 
@@ -94,8 +100,9 @@ def make_block_rc(index_list: Sequence[Tuple[int, int]], device) -> torch.Tensor
 def score_accumulate(acc: torch.Tensor, grad: torch.Tensor) -> None:
     """acc += grad (fp32 accumulator, any supported grad dtype). fine_tune.py:724-765."""
     require_cuda(acc, grad)
-    assert acc.dtype == torch.float32 and acc.is_contiguous() and grad.is_contiguous()
-    assert acc.numel() == grad.numel()
+    _req(acc.dtype == torch.float32 and acc.is_contiguous() and grad.is_contiguous(),
+         "acc.dtype == torch.float32 and acc.is_contiguous() and grad.is_contiguous()")
+    _req(acc.numel() == grad.numel(), "acc.numel() == grad.numel()")
     check(load().smt_score_accumulate(ptr(acc), ptr(grad), dtype_id(grad.dtype), grad.numel(), _st(acc)),
           "smt_score_accumulate")
     _count()
@@ -104,9 +111,11 @@ def score_accumulate(acc: torch.Tensor, grad: torch.Tensor) -> None:
 def block_sum_accumulate(block_sums: torch.Tensor, grad: torch.Tensor, block: int) -> None:
     """block_sums[R/b, C/b] += per-block signed sums of grad[R, C]."""
     require_cuda(block_sums, grad)
-    assert grad.dim() == 2 and grad.stride(1) == 1 and block_sums.dtype == torch.float32
+    _req(grad.dim() == 2 and grad.stride(1) == 1 and block_sums.dtype == torch.float32,
+         "grad.dim() == 2 and grad.stride(1) == 1 and block_sums.dtype == torch.float32")
     R, Cc = grad.shape
-    assert block_sums.is_contiguous() and block_sums.numel() == (R // block) * (Cc // block)
+    _req(block_sums.is_contiguous() and block_sums.numel() == (R // block) * (Cc // block),
+         "block_sums.is_contiguous() and block_sums.numel() == (R // block) * (Cc // block)")
     check(load().smt_block_sum_accumulate(ptr(block_sums), ptr(grad), dtype_id(grad.dtype), R, Cc,
                                           grad.stride(0), block, _st(grad)), "smt_block_sum_accumulate")
     _count()
@@ -125,7 +134,8 @@ def block_score_reduce(acc: torch.Tensor, block: int, strategy: str = "mean_abs"
                        out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """scores[R/b, C/b] of an fp32 [R, C] matrix. smt_helper.py:55-78, 233-251."""
     require_cuda(acc)
-    assert acc.dim() == 2 and acc.dtype == torch.float32 and acc.stride(1) == 1
+    _req(acc.dim() == 2 and acc.dtype == torch.float32 and acc.stride(1) == 1,
+         "acc.dim() == 2 and acc.dtype == torch.float32 and acc.stride(1) == 1")
     if strategy not in STRATEGY_IDS:
         raise _lib.SMTLibraryError(f"unknown calculate_strategy {strategy!r}")
     R, Cc = acc.shape
@@ -140,9 +150,10 @@ def block_score_reduce(acc: torch.Tensor, block: int, strategy: str = "mean_abs"
 def act_score_accumulate(acc: torch.Tensor, x: torch.Tensor) -> None:
     """acc[S, C] += sum_b |x[b, S, C]|. fine_tune.py:649-678 (reduced over batch)."""
     require_cuda(acc, x)
-    assert x.dim() == 3 and x.is_contiguous() and acc.is_contiguous() and acc.dtype == torch.float32
+    _req(x.dim() == 3 and x.is_contiguous() and acc.is_contiguous() and acc.dtype == torch.float32,
+         "x.dim() == 3 and x.is_contiguous() and acc.is_contiguous() and acc.dtype == torch.float32")
     Bn, S, Cc = x.shape
-    assert tuple(acc.shape) == (S, Cc)
+    _req(tuple(acc.shape) == (S, Cc), "tuple(acc.shape) == (S, Cc)")
     check(load().smt_act_score_accumulate(ptr(acc), ptr(x), dtype_id(x.dtype), Bn, S, Cc, _st(x)),
           "smt_act_score_accumulate")
     _count()
@@ -150,7 +161,8 @@ def act_score_accumulate(acc: torch.Tensor, x: torch.Tensor) -> None:
 
 def channel_score_reduce(acc: torch.Tensor, strategy: str = "mean_abs") -> torch.Tensor:
     require_cuda(acc)
-    assert acc.dim() == 2 and acc.is_contiguous() and acc.dtype == torch.float32
+    _req(acc.dim() == 2 and acc.is_contiguous() and acc.dtype == torch.float32,
+         "acc.dim() == 2 and acc.is_contiguous() and acc.dtype == torch.float32")
     if strategy not in STRATEGY_IDS:
         raise _lib.SMTLibraryError(f"unknown calculate_strategy {strategy!r}")
     S, Cc = acc.shape
@@ -168,10 +180,12 @@ def topk_blocks(scores: torch.Tensor, seg_offsets: Sequence[int], seg_k: Sequenc
                 inv_rank: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, list]:
     """Segmented top-k. Returns (flat int32 indices on device, per-segment output offsets (host list))."""
     require_cuda(scores, tiebreak_rank, inv_rank)
-    assert scores.dtype == torch.float32 and scores.is_contiguous()
+    _req(scores.dtype == torch.float32 and scores.is_contiguous(),
+         "scores.dtype == torch.float32 and scores.is_contiguous()")
     n = scores.numel()
     nseg = len(seg_k)
-    assert len(seg_offsets) == nseg + 1 and seg_offsets[-1] == n
+    _req(len(seg_offsets) == nseg + 1 and seg_offsets[-1] == n,
+         "len(seg_offsets) == nseg + 1 and seg_offsets[-1] == n")
     out_offsets = [0]
     for s in range(nseg):
         length = seg_offsets[s + 1] - seg_offsets[s]
@@ -185,8 +199,10 @@ def topk_blocks(scores: torch.Tensor, seg_offsets: Sequence[int], seg_k: Sequenc
     ws_bytes = lib.smt_topk_workspace_bytes(n)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
     if tiebreak_rank is not None:
-        assert tiebreak_rank.dtype == torch.int32 or tiebreak_rank.dtype == torch.uint32
-        assert inv_rank is not None and inv_rank.numel() == n and tiebreak_rank.numel() == n
+        _req(tiebreak_rank.dtype == torch.int32 or tiebreak_rank.dtype == torch.uint32,
+             "tiebreak_rank.dtype == torch.int32 or tiebreak_rank.dtype == torch.uint32")
+        _req(inv_rank is not None and inv_rank.numel() == n and tiebreak_rank.numel() == n,
+             "inv_rank is not None and inv_rank.numel() == n and tiebreak_rank.numel() == n")
     check(lib.smt_topk_blocks(ptr(scores), ptr(tiebreak_rank), ptr(inv_rank), n, ptr(d_off), ptr(d_k),
                               ptr(d_out_off), nseg, ptr(out), ptr(ws), ws_bytes, _st(scores)),
           "smt_topk_blocks")
@@ -199,7 +215,8 @@ def topk_blocks(scores: torch.Tensor, seg_offsets: Sequence[int], seg_k: Sequenc
 def block_gather(table: torch.Tensor, n_blocks: int, block: int, compact: torch.Tensor) -> None:
     """compact[i] <- W_i block. smt.py:317-325."""
     require_cuda(table, compact)
-    assert compact.is_contiguous() and compact.numel() == n_blocks * block * block
+    _req(compact.is_contiguous() and compact.numel() == n_blocks * block * block,
+         "compact.is_contiguous() and compact.numel() == n_blocks * block * block")
     check(load().smt_block_gather(ptr(table), n_blocks, block, compact.element_size(), ptr(compact),
                                   _st(compact)), "smt_block_gather")
     _count()
@@ -208,9 +225,55 @@ def block_gather(table: torch.Tensor, n_blocks: int, block: int, compact: torch.
 def block_scatter(table: torch.Tensor, n_blocks: int, block: int, compact: torch.Tensor) -> None:
     """W_i block <- compact[i]. smt.py:332-341."""
     require_cuda(table, compact)
-    assert compact.is_contiguous() and compact.numel() == n_blocks * block * block
+    _req(compact.is_contiguous() and compact.numel() == n_blocks * block * block,
+         "compact.is_contiguous() and compact.numel() == n_blocks * block * block")
     check(load().smt_block_scatter(ptr(table), n_blocks, block, compact.element_size(), ptr(compact),
                                    _st(compact)), "smt_block_scatter")
+    _count()
+
+
+# ---- channel (input-column) movement ------------------------------------------------------------------------
+
+def make_channel_idx(index_list, device) -> torch.Tensor:
+    """int32 device copy of a channel index list."""
+    return torch.tensor([int(i) for i in index_list], dtype=torch.int32, device="cpu").to(device)
+
+
+def channel_gather(x2: torch.Tensor, idx: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[t, i] = x2[t, idx[i]] — the packed selected input channels (smt.py:240-247)."""
+    require_cuda(x2, idx)
+    _req(x2.dim() == 2 and x2.stride(1) == 1 and idx.dtype == torch.int32 and idx.is_contiguous(),
+         "x2.dim() == 2 and x2.stride(1) == 1 and idx.dtype == torch.int32 and idx.is_contiguous()")
+    T, n = x2.shape[0], idx.numel()
+    if out is None:
+        out = torch.empty(T, n, dtype=x2.dtype, device=x2.device)
+    _req(out.is_contiguous() and out.shape == (T, n) and out.dtype == x2.dtype,
+         "out.is_contiguous() and out.shape == (T, n) and out.dtype == x2.dtype")
+    check(load().smt_channel_gather(ptr(x2), T, x2.stride(0), ptr(idx), n, x2.element_size(), ptr(out), _st(x2)),
+          "smt_channel_gather")
+    _count()
+    return out
+
+
+def _column_args(W, idx, compact):
+    require_cuda(W, idx, compact)
+    _req(W.dim() == 2 and W.stride(1) == 1 and idx.dtype == torch.int32 and idx.is_contiguous(),
+         "W.dim() == 2 and W.stride(1) == 1 and idx.dtype == torch.int32 and idx.is_contiguous()")
+    n = idx.numel()
+    _req(compact.is_contiguous() and compact.shape == (n, W.shape[0]) and compact.dtype == W.dtype,
+         "compact.is_contiguous() and compact.shape == (n, W.shape[0]) and compact.dtype == W.dtype")
+    return ptr(W), W.stride(0), W.shape[0], W.shape[1], ptr(idx), n, W.element_size(), ptr(compact), _st(W)
+
+
+def column_gather(W: torch.Tensor, idx: torch.Tensor, compact: torch.Tensor) -> None:
+    """compact[i, :] <- W[:, idx[i]]."""
+    check(load().smt_column_gather(*_column_args(W, idx, compact)), "smt_column_gather")
+    _count()
+
+
+def column_scatter(W: torch.Tensor, idx: torch.Tensor, compact: torch.Tensor) -> None:
+    """W[:, idx[i]] <- compact[i, :]."""
+    check(load().smt_column_scatter(*_column_args(W, idx, compact)), "smt_column_scatter")
     _count()
 
 
@@ -241,15 +304,19 @@ def block_grad_gemm(x2d: torch.Tensor, dy2d: torch.Tensor, block_rc: torch.Tenso
     x2d: [T, in], dy2d: [T, out] (unit column stride, same dtype); block_rc: int32 [n, 2] on device.
     """
     require_cuda(x2d, dy2d, block_rc)
-    assert x2d.dim() == 2 and dy2d.dim() == 2 and x2d.shape[0] == dy2d.shape[0]
-    assert x2d.stride(1) == 1 and dy2d.stride(1) == 1 and x2d.dtype == dy2d.dtype
-    assert block_rc.dtype == torch.int32 and block_rc.is_contiguous()
+    _req(x2d.dim() == 2 and dy2d.dim() == 2 and x2d.shape[0] == dy2d.shape[0],
+         "x2d.dim() == 2 and dy2d.dim() == 2 and x2d.shape[0] == dy2d.shape[0]")
+    _req(x2d.stride(1) == 1 and dy2d.stride(1) == 1 and x2d.dtype == dy2d.dtype,
+         "x2d.stride(1) == 1 and dy2d.stride(1) == 1 and x2d.dtype == dy2d.dtype")
+    _req(block_rc.dtype == torch.int32 and block_rc.is_contiguous(),
+         "block_rc.dtype == torch.int32 and block_rc.is_contiguous()")
     n = block_rc.shape[0]
     T = x2d.shape[0]
     if out is None:
         out = torch.empty((n * block, block), dtype=out_dtype or dy2d.dtype, device=x2d.device)
         accumulate = False
-    assert out.is_contiguous() and out.numel() == n * block * block
+    _req(out.is_contiguous() and out.numel() == n * block * block,
+         "out.is_contiguous() and out.numel() == n * block * block")
     lib = load()
     in_id = dtype_id(x2d.dtype)
     ws_bytes = lib.smt_block_grad_gemm_workspace_bytes(n, block, T, in_id)
@@ -277,7 +344,7 @@ def block_grad_gemm_plan(n_blocks: int, block: int, T: int, dtype: torch.dtype) 
 def grad_sqnorm(grad: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Deterministic sum of squares of a flat gradient buffer -> fp32 scalar tensor on device."""
     require_cuda(grad)
-    assert grad.is_contiguous()
+    _req(grad.is_contiguous(), "grad.is_contiguous()")
     if out is None:
         out = torch.empty((1,), dtype=torch.float32, device=grad.device)
     lib = load()
@@ -297,8 +364,9 @@ def compact_adam(master: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.
     """One fused AdamW step over flat compact state (+ clip, + dense write-back). See smt_b200.h."""
     require_cuda(master, exp_avg, exp_avg_sq, grad, sqnorm, compact_out, table)
     for t in (master, exp_avg, exp_avg_sq):
-        assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == grad.numel()
-    assert grad.is_contiguous()
+        _req(t.dtype == torch.float32 and t.is_contiguous() and t.numel() == grad.numel(),
+             "t.dtype == torch.float32 and t.is_contiguous() and t.numel() == grad.numel()")
+    _req(grad.is_contiguous(), "grad.is_contiguous()")
     bc1 = 1.0 - beta1 ** step
     bc2 = 1.0 - beta2 ** step
     _count()
@@ -330,9 +398,11 @@ class BlockGradBatch:
 
     def add(self, x2d: torch.Tensor, dy2d: torch.Tensor, index_list, out: torch.Tensor, block: int) -> None:
         require_cuda(x2d, dy2d, out)
-        assert x2d.dim() == 2 and dy2d.dim() == 2 and x2d.shape[0] == dy2d.shape[0] and x2d.dtype == dy2d.dtype
-        assert x2d.stride(1) == 1 and dy2d.stride(1) == 1 and out.is_contiguous()
-        assert out.numel() == len(index_list) * block * block
+        _req(x2d.dim() == 2 and dy2d.dim() == 2 and x2d.shape[0] == dy2d.shape[0] and x2d.dtype == dy2d.dtype,
+             "x2d.dim() == 2 and dy2d.dim() == 2 and x2d.shape[0] == dy2d.shape[0] and x2d.dtype == dy2d.dtype")
+        _req(x2d.stride(1) == 1 and dy2d.stride(1) == 1 and out.is_contiguous(),
+             "x2d.stride(1) == 1 and dy2d.stride(1) == 1 and out.is_contiguous()")
+        _req(out.numel() == len(index_list) * block * block, "out.numel() == len(index_list) * block * block")
         self.problems.append((x2d, dy2d, [(int(r), int(c)) for r, c in index_list], out, int(block)))
 
     def flush(self, accumulate: bool = True) -> int:

@@ -21,9 +21,10 @@ What changed underneath:
     batch reduction and a slice copy per block, rounding to bf16 per batch entry;
   * importing this module does not call `deepspeed.init_distributed()` (the reference does, smt.py:20).
 
-The channel-sparsity twins (`convert_linear_layer_to_channel_sparsity`, `freeze_unselected_channel_layer`) are
-importable but raise: the reference implementation selects rows and differentiates columns and fails for every
-non-square weight, so there is nothing well-defined to be compatible with.
+The channel-sparsity twins (`LinearLayer_ChannelSparsity`, `linearChannel`, `convert_linear_layer_to_channel_sparsity`,
+`freeze_unselected_channel_layer`; smt.py:25-80, 185-296, 748-831) keep the reference's names and signatures but use
+COLUMN semantics: the reference selects input channels, differentiates weight columns and copies weight rows, which
+fails for every non-square weight.  Its gradient formula is kept exactly.
 """
 from __future__ import annotations
 
@@ -387,12 +388,164 @@ def get_optimizer_qk_augment_grouped_parameters(
                                module_name_list)
 
 
-def _channel_path_unsupported(*_args, **_kwargs):
-    raise NotImplementedError(
-        "channel sparsity (smt.py:25-80, 185-296, 748-831) is not part of the B200 hot path: the reference "
-        "implementation selects weight rows but differentiates columns and fails for non-square weights. "
-        "Channel *scoring and selection* are available as smt_helper.select_channel_based_on_activation.")
+# ---- channel sparsity (the activation-selected path, done consistently) -----------------
+#
+# The reference's LinearLayer_ChannelSparsity (smt.py:185-296) is selected by INPUT-channel activation scores
+# (smt_helper.py:149-230), computes the gradient of weight COLUMNS `partial_input^T @ grad_output` (smt.py:283-284)
+# but initialises from and writes back to weight ROWS (smt.py:198-200, 208-211): it fails for every non-square weight
+# and trains the wrong entries for square ones.  Here channel i owns COLUMN index_list[i] of W; `selected_weight` is
+# [n, out_features] (row i = W[:, index_list[i]]), so the gradient formula is the reference's, bit for bit in fp32.
+
+_idx_cache: Dict[Tuple[int, torch.device], Tuple[tuple, torch.Tensor]] = {}
 
 
-convert_linear_layer_to_channel_sparsity = _channel_path_unsupported
-freeze_unselected_channel_layer = _channel_path_unsupported
+def _channel_idx_for(index_list, device) -> torch.Tensor:
+    snap = tuple(int(i) for i in index_list)
+    key = (id(index_list), device)
+    hit = _idx_cache.get(key)
+    if hit is not None and hit[0] == snap:
+        return hit[1]
+    t = ops.make_channel_idx(snap, device)
+    if len(_idx_cache) > 4096:
+        _idx_cache.clear()
+    _idx_cache[key] = (snap, t)
+    return t
+
+
+class linearChannel(torch.autograd.Function):
+    """y = x W^T with a gradient only for the selected input channels.  Reference: smt.py:220-296.
+
+    forward(ctx, input, selected_weight, channel_index_list, weight)
+    backward -> (grad_input, grad_weight [n, out_features], None, None)
+    """
+
+    @staticmethod
+    def forward(ctx, input, selected_weight, channel_index_list, weight):
+        x2 = input.reshape(-1, input.shape[-1])
+        if x2.stride(-1) != 1:
+            x2 = x2.contiguous()
+        idx = _channel_idx_for(channel_index_list, x2.device)
+        partial = ops.channel_gather(x2, idx)              # [T, n] packed copy, ONE launch (smt.py:240-247)
+        ctx.save_for_backward(partial, weight)
+        return torch.matmul(input, weight.t())            # smt.py:257
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        partial, weight = ctx.saved_tensors
+        grad_input = grad_weight = None
+        if ctx.needs_input_grad[1]:
+            dy2 = grad_output.reshape(-1, grad_output.shape[-1])
+            # smt.py:283-284: sum over the batch of partial^T @ dy — here one plain TN GEMM over all tokens
+            # (library GEMM, fp32 accumulation, one rounding)
+            grad_weight = torch.matmul(partial.t().to(dy2.dtype), dy2)
+        if ctx.needs_input_grad[0]:
+            grad_input = torch.matmul(grad_output, weight)                                      # smt.py:286
+        return grad_input, grad_weight, None, None
+
+
+class LinearLayer_ChannelSparsity(nn.Module):
+    """Linear layer whose only trainable parameter is a compact copy of its selected input channels (weight columns).
+    Reference: smt.py:185-217 (same constructor signature and attribute names; column semantics, see above)."""
+
+    def __init__(self, weight, bias=None, index_list=[]):
+        super().__init__()
+        if not weight.is_cuda:
+            raise SMTLibraryError("LinearLayer_ChannelSparsity needs its weight on a CUDA device: the SMT kernels "
+                                  "have no CPU fallback")
+        self.weight = weight
+        self.weight.requires_grad = False                 # smt.py:191
+        self.bias = bias                                  # kept but unused, like smt.py:192,214
+        self.index_list = index_list
+        seen = set()
+        for i in index_list:
+            if not 0 <= int(i) < weight.shape[1]:
+                raise IndexError(f"channel {i} outside a weight with {weight.shape[1]} input channels")
+            if int(i) in seen:
+                raise ValueError(f"channel {i} selected twice")
+            seen.add(int(i))
+        n = len(index_list)
+        compact = torch.empty(n, weight.shape[0], dtype=weight.dtype, device=weight.device)
+        if n:
+            ops.column_gather(weight.data, _channel_idx_for(index_list, weight.device), compact)
+        self.selected_weight = nn.Parameter(compact, requires_grad=True)
+        self.fn = linearChannel.apply
+        self._synced = (self.selected_weight.data_ptr(), self.selected_weight._version)
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self._synced = None
+        return out
+
+    def sync_weight(self, force: bool = False) -> None:
+        """compact -> dense write-back (smt.py:208-211) — one launch, skipped when nothing changed."""
+        state = (self.selected_weight.data_ptr(), self.selected_weight._version)
+        if force or self._synced != state:
+            if len(self.index_list):
+                sw = self.selected_weight.data
+                if sw.dtype != self.weight.dtype:
+                    sw = sw.to(self.weight.dtype)
+                ops.column_scatter(self.weight.data, _channel_idx_for(self.index_list, self.weight.device),
+                                   sw.contiguous())
+            self._synced = state
+
+    def forward(self, x):
+        self.sync_weight()
+        return self.fn(x, self.selected_weight, self.index_list, self.weight)   # smt.py:213
+
+
+def convert_linear_layer_to_channel_sparsity(model,
+                                             selected_channel,
+                                             selected_channel_attention,
+                                             part_module_name=['.layers']):
+    """Reference: smt.py:25-80.  MLP Linears are looked up in `selected_channel`, attention Linears (q/k/v/o by
+    substring) in `selected_channel_attention`; only weights that still require grad are converted."""
+    names = [name for name, module in model.named_modules()
+             if isinstance(module, nn.Linear) and any(part in name for part in part_module_name)]
+    for name in names:
+        for marker, kind_of, table in (("mlp", _mlp_kind, selected_channel),
+                                       ("self_attn", _attn_kind, selected_channel_attention)):
+            if marker not in name:
+                continue
+            module = _getattr_path(model, name)
+            if not isinstance(module, nn.Linear) or not module.weight.requires_grad:
+                continue
+            _rank0_print(f"Module Test: {name}")
+            index_list = table[(kind_of(name), _layer_of(name))]
+            sparse = LinearLayer_ChannelSparsity(module.weight, bias=None, index_list=index_list)
+            _setattr_path(model, name, sparse.to(module.weight.device).to(module.weight.dtype))
+    return model
+
+
+def convert_channel_sparsity_to_linear_layer(model, part_module_name=['.layers']):
+    """Write the trained channels back and restore plain nn.Linear modules (the channel twin of smt.py:416-457; the
+    reference has no such function for channels)."""
+    names = [name for name, module in model.named_modules()
+             if isinstance(module, LinearLayer_ChannelSparsity) and any(part in name for part in part_module_name)]
+    for name in names:
+        module = _getattr_path(model, name)
+        module.sync_weight(force=True)
+        out_f, in_f = module.weight.shape
+        linear = nn.Linear(in_f, out_f, bias=False, device="meta")
+        linear = linear.to_empty(device=module.weight.device).to(module.weight.dtype)
+        linear.weight = module.weight
+        _setattr_path(model, name, linear)
+    return model
+
+
+def freeze_unselected_channel_layer(model,
+                                    select_parameters,
+                                    select_attention_parameters,
+                                    mixture=False):
+    """Reference: smt.py:748-831.  Attention names resolve to q/k/v only here (o_proj -> None, smt.py:778,811)."""
+    for name, param in model.named_parameters():
+        layer = _layer_of(name)
+        if "mlp" in name:
+            trainable = (_mlp_kind(name), layer) in select_parameters.keys()
+        elif "self_attn" in name:
+            kind = next((k for k in ("q_proj", "k_proj", "v_proj") if k in name), None)
+            table = select_parameters if mixture else select_attention_parameters
+            trainable = (kind, layer) in table.keys()
+        else:
+            trainable = False
+        param.requires_grad = trainable
+    return model

@@ -560,3 +560,109 @@ def test_mixture_mode_conversion(api):
     model(input_ids=ids, labels=ids, use_cache=False).loss.backward()
     g = model.model.layers[1].mlp.gate_proj.selected_weight.grad
     assert g is not None and tuple(g.shape) == (512, 256) and g.abs().sum() > 0
+
+
+@pytest.mark.parametrize("case", load_golden("linearchannel_cases.pt"), ids=lambda c: c["spec"]["name"])
+def test_linear_layer_channel_sparsity_golden(api, case):
+    """Square weights = the shapes the reference's channel layer runs on: y, grad_input and the [n, out] channel
+    gradient must match the reference's outputs; the compact parameter holds the selected COLUMNS."""
+    M, _H = api
+    spec = case["spec"]
+    x, dy, w, idx = case["x"], case["dy"], case["w"], case["index_list"]
+    layer = M.LinearLayer_ChannelSparsity(torch.nn.Parameter(w.clone().cuda()), bias=None, index_list=idx)
+    assert torch.equal(layer.selected_weight.detach().cpu(), O.gather_columns(w, idx))       # gather: exact
+    assert layer.selected_weight.requires_grad and not layer.weight.requires_grad
+    xin = x.clone().cuda().requires_grad_(True)
+    y = layer(xin)
+    y.backward(dy.cuda())
+    gw, gi = layer.selected_weight.grad.cpu(), xin.grad.cpu()
+    assert gw.shape == case["grad_weight"].shape and gw.dtype == case["grad_weight"].dtype
+    truth = x.reshape(-1, x.shape[-1])[:, idx].double().t() @ dy.reshape(-1, dy.shape[-1]).double()
+    scale = truth.abs().max().item()
+    if spec["dtype"] == "float32":
+        assert (gw - case["grad_weight"]).abs().max().item() <= 1e-5 * scale
+        assert torch.allclose(y.detach().cpu(), case["y"], rtol=1e-4, atol=1e-5)
+        assert torch.allclose(gi, case["grad_input"], rtol=1e-4, atol=1e-5)
+    else:
+        err = (gw.double() - truth).abs().max().item() / scale
+        ref_err = (case["grad_weight"].double() - truth).abs().max().item() / scale
+        assert err <= 2 ** -7 and err <= ref_err * 1.10 + 1e-6                               # no worse than the reference
+        assert (y.detach().cpu().float() - case["y"].float()).abs().max() <= 2 ** -7 * case["y"].float().abs().max()
+        assert (gi.float() - case["grad_input"].float()).abs().max() <= 2 ** -6 * case["grad_input"].float().abs().max()
+
+
+def test_channel_sparsity_non_square_training_and_merge(api):
+    """What the reference cannot do: a 384 x 640 weight.  Column gather / scatter are exact against the oracle's
+    column restatement, the gradient matches it, SMTAdam updates only the selected columns and the write-back lands
+    before the next forward; convert_channel_sparsity_to_linear_layer merges."""
+    M, _H = api
+    from sparse_matrix_tuning_b200.optim import SMTAdam
+    torch.manual_seed(7)
+    B, S, fin, fout = 3, 50, 640, 384
+    idx = [639, 0, 5, 64, 63, 320, 17]
+    w = (torch.randn(fout, fin) * 0.05).bfloat16()
+    x = torch.randn(B, S, fin).bfloat16()
+    dy = torch.randn(B, S, fout).bfloat16()
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.layers = torch.nn.ModuleList([torch.nn.Linear(fin, fout, bias=False)])
+
+    net = Net().cuda().bfloat16()
+    with torch.no_grad():
+        net.layers[0].weight.copy_(w.cuda())
+    layer = M.LinearLayer_ChannelSparsity(net.layers[0].weight, bias=None, index_list=idx)
+    net.layers[0] = layer
+    assert torch.equal(layer.selected_weight.detach().cpu(), O.gather_columns(w, idx))
+    opt = SMTAdam([layer.selected_weight], lr=1e-2, betas=(0.9, 0.95), max_grad_norm=1.0)
+    xin = x.cuda().requires_grad_(True)
+    y = layer(xin)
+    y.backward(dy.cuda())
+    gi_ref, gw_ref = O.linearchannel_backward(x.float(), dy.float(), w.float(), idx)
+    scale = gw_ref.abs().max().item()
+    assert (layer.selected_weight.grad.float().cpu() - gw_ref).abs().max().item() <= 2 ** -7 * scale
+    assert (xin.grad.float().cpu() - gi_ref).abs().max().item() <= 2 ** -6 * gi_ref.abs().max().item()
+    before = layer.weight.detach().clone()
+    opt.step()
+    y2 = layer(x.cuda())                                            # forward re-scatters the updated columns
+    after = layer.weight.detach()
+    keep = [c for c in range(fin) if c not in idx]
+    assert torch.equal(after[:, keep], before[:, keep])             # untouched columns are bit-identical
+    assert torch.equal(after[:, idx].t().contiguous(), layer.selected_weight.detach())
+    assert not torch.equal(after[:, idx], before[:, idx])
+    assert torch.equal(y2, torch.matmul(x.cuda(), after.t()))
+    M.convert_channel_sparsity_to_linear_layer(net, part_module_name=['layers'])
+    assert isinstance(net.layers[0], torch.nn.Linear) and net.layers[0].weight.data_ptr() == after.data_ptr()
+
+
+def test_channel_freeze_and_convert_on_tiny_llama(api):
+    """fine_tune.py:511-520: freeze_unselected_channel_layer + convert_linear_layer_to_channel_sparsity on a tiny
+    LLaMA (rectangular k/v and MLP weights included); one training step decreases nothing it should not touch."""
+    M, H = api
+    from transformers import LlamaConfig, LlamaForCausalLM
+    cfg = LlamaConfig(hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=4,
+                      num_key_value_heads=2, vocab_size=256)
+    torch.manual_seed(0)
+    model = LlamaForCausalLM(cfg).cuda()
+    sel_mlp = {("gate_proj", 0): [1, 2, 100], ("down_proj", 1): [3, 255]}
+    sel_attn = {("q_proj", 1): [5, 6], ("v_proj", 0): [0, 127]}
+    model = M.freeze_unselected_channel_layer(model, sel_mlp, sel_attn)
+    model = M.convert_linear_layer_to_channel_sparsity(model, sel_mlp, sel_attn)
+    converted = {n for n, m in model.named_modules() if isinstance(m, M.LinearLayer_ChannelSparsity)}
+    assert converted == {"model.layers.0.mlp.gate_proj", "model.layers.1.mlp.down_proj",
+                         "model.layers.1.self_attn.q_proj", "model.layers.0.self_attn.v_proj"}
+    trainable = {n: p for n, p in model.named_parameters() if p.requires_grad}
+    assert all(n.endswith("selected_weight") for n in trainable) and len(trainable) == 4
+    assert trainable["model.layers.0.self_attn.v_proj.selected_weight"].shape == (2, 64)     # [n, out_features]
+    assert trainable["model.layers.1.mlp.down_proj.selected_weight"].shape == (2, 128)
+    groups = M.get_optimizer_sparse_grouped_parameters(model, 0.0, 1e-3)
+    opt = torch.optim.AdamW(groups, lr=1e-3)
+    ids = torch.randint(0, 256, (2, 16), device="cuda")
+    losses = []
+    for _ in range(3):
+        out = model(input_ids=ids, labels=ids)
+        out.loss.backward()
+        opt.step(); opt.zero_grad()
+        losses.append(out.loss.item())
+    assert losses[-1] < losses[0]

@@ -148,7 +148,8 @@ def test_public_api_names_and_signatures():
     for name in ("convert_linear_layer_to_matrix_sparsity", "get_optimizer_sparse_grouped_parameters",
                  "get_optimizer_qk_augment_grouped_parameters", "freeze_unselected_matrix_layer",
                  "freeze_unselected_channel_layer", "convert_linear_layer_to_channel_sparsity",
-                 "convert_matrix_sparsity_to_linear_layer", "LinearLayer_MatrixSparsity", "linearZ"):
+                 "convert_matrix_sparsity_to_linear_layer", "LinearLayer_MatrixSparsity", "linearZ",
+                 "LinearLayer_ChannelSparsity", "linearChannel"):
         assert hasattr(M, name)
     for name in ("select_submatrix_based_on_grads", "get_blocks", "get_named_linears",
                  "select_channel_based_on_activation"):
@@ -158,7 +159,8 @@ def test_public_api_names_and_signatures():
         S, RH = load_reference()
         for mod, ref, names in ((M, S, ("convert_linear_layer_to_matrix_sparsity", "freeze_unselected_matrix_layer",
                                         "get_optimizer_sparse_grouped_parameters", "convert_matrix_sparsity_to_linear_layer",
-                                        "get_optimizer_qk_augment_grouped_parameters")),
+                                        "get_optimizer_qk_augment_grouped_parameters",
+                                        "convert_linear_layer_to_channel_sparsity", "freeze_unselected_channel_layer")),
                                 (H, RH, ("select_submatrix_based_on_grads", "select_channel_based_on_activation"))):
             for n in names:
                 a, b = inspect.signature(getattr(mod, n)), inspect.signature(getattr(ref, n))
@@ -166,8 +168,29 @@ def test_public_api_names_and_signatures():
                 assert [p.default for p in a.parameters.values()] == [p.default for p in b.parameters.values()], n
         assert list(inspect.signature(M.LinearLayer_MatrixSparsity.__init__).parameters) == \
             list(inspect.signature(S.LinearLayer_MatrixSparsity.__init__).parameters)
-    with pytest.raises(NotImplementedError):
-        M.convert_linear_layer_to_channel_sparsity(None, {}, {})
+        assert list(inspect.signature(M.LinearLayer_ChannelSparsity.__init__).parameters) == \
+            list(inspect.signature(S.LinearLayer_ChannelSparsity.__init__).parameters)
+
+
+def test_freeze_unselected_channel_layer_matches_reference():
+    """smt.py:748-831 on a tiny LLaMA: same requires_grad pattern as the reference, with and without mixture."""
+    if not reference_available():
+        pytest.skip("reference not mounted")
+    from transformers import LlamaConfig, LlamaForCausalLM
+    from sparse_matrix_tuning_b200.smt import smt as M
+    S, _ = load_reference()
+    cfg = LlamaConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+                      num_key_value_heads=2, vocab_size=128)
+    sel_mlp = {("gate_proj", 0): [1, 2], ("down_proj", 1): [3]}
+    sel_attn = {("q_proj", 1): [5], ("v_proj", 0): [0, 7], ("o_proj", 0): [1]}
+    for mixture in (False, True):
+        torch.manual_seed(0)
+        a, b = LlamaForCausalLM(cfg), LlamaForCausalLM(cfg)
+        merged = {**sel_mlp, **sel_attn}
+        S.freeze_unselected_channel_layer(a, merged if mixture else sel_mlp, sel_attn, mixture=mixture)
+        M.freeze_unselected_channel_layer(b, merged if mixture else sel_mlp, sel_attn, mixture=mixture)
+        assert [(n, p.requires_grad) for n, p in a.named_parameters()] == \
+            [(n, p.requires_grad) for n, p in b.named_parameters()]
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the behaviour WITHOUT a GPU")

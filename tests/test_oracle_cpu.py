@@ -55,6 +55,21 @@ def test_linearz_matches_reference_golden(case):
     assert torch.equal(gi, case["grad_input"])
 
 
+@pytest.mark.parametrize("case", load_golden("linearchannel_cases.pt"), ids=lambda c: c["spec"]["name"])
+def test_linearchannel_matches_reference_golden(case):
+    """The reference's channel layer on square weights (the only shapes it runs on): same y, grad_input and [n, out]
+    channel gradient, bit for bit.  The column gather / scatter restatement round-trips."""
+    x, dy, w, idx = case["x"], case["dy"], case["w"], case["index_list"]
+    assert torch.equal(O.linearz_forward(x, w), case["y"])
+    gi, gw = O.linearchannel_backward(x, dy, w, idx)
+    assert torch.equal(gw, case["grad_weight"]) and torch.equal(gi, case["grad_input"])
+    cols = O.gather_columns(w, idx)
+    assert cols.shape == (len(idx), w.shape[0]) and torch.equal(cols[0], w[:, idx[0]])
+    w2 = O.scatter_columns(w.clone(), cols * 2, idx)
+    keep = [c for c in range(w.shape[1]) if c not in idx]
+    assert torch.equal(w2[:, idx], w[:, idx] * 2) and torch.equal(w2[:, keep], w[:, keep])
+
+
 def test_config1_budget_and_dims_match_golden():
     gold = load_golden("config1_e2e.pt")
     model, _ = GI.make_config1()
