@@ -169,8 +169,9 @@ typedef struct smt_gemm_item {
   int32_t  col;      /* block column (in_features  / b index)            */
   int64_t  out_off;  /* element offset of this block's [b, b] output     */
 } smt_gemm_item;
+/* `block` = the block size of the launch the descriptor will be used in (it fixes the TMA box height). */
 SMT_API int smt_encode_operand_map(void* map_host, const void* base, int64_t features, int64_t T, int64_t ld,
-                                   int dtype);
+                                   int dtype, int block);
 SMT_API size_t smt_block_grad_gemm_grouped_workspace_bytes(int n_items, int n_paired, int block, int64_t T);
 SMT_API int smt_block_grad_gemm_grouped(const void* maps, const smt_gemm_item* items, int n_items, int n_paired,
                                         int64_t T, int block, int in_dtype, void* out_base, int out_dtype,

@@ -34,34 +34,56 @@
 namespace smt {
 namespace {
 
+// Tokens per pipeline stage (multiples of 16, <= 256 = the tallest TMA box), per block size.  Every stage carries a
+// fixed cost (~100-150 clk per TMA box plus the barrier round trip) that a whole-block b = 256 tile hides behind
+// 1 024 clk of UMMA work; the small tiles do not, so they take 128-token stages (half as many boxes and barrier
+// round trips per token; +23-56 % on B200, profiles/r01_kernels.md section 1c).
 #ifndef SMT_GEMM_KTILE
-#define SMT_GEMM_KTILE 64                     // tokens per pipeline stage (multiple of 16)
+#define SMT_GEMM_KTILE 64                     // b = 256
+#endif
+#ifndef SMT_GEMM_KTILE_128
+#define SMT_GEMM_KTILE_128 128                // b = 128
+#endif
+#ifndef SMT_GEMM_KTILE_64
+#define SMT_GEMM_KTILE_64 256                 // b = 64
+#endif
+#ifndef SMT_GEMM_B64_ALIAS
+#define SMT_GEMM_B64_ALIAS 1                  // b = 64: no shared-memory slot for the unused upper half of the M=128 operand
 #endif
 #ifndef SMT_GEMM_MAX_STAGES
 #define SMT_GEMM_MAX_STAGES 8
 #endif
-constexpr int kKTile = SMT_GEMM_KTILE;        // tokens per pipeline stage
-constexpr int kChunkBytes = kKTile * 128;     // one {64 features x K_TILE tokens} TMA box of 16-bit data
+constexpr int ktile_for(int block) {
+  return block == 256 ? SMT_GEMM_KTILE : block == 128 ? SMT_GEMM_KTILE_128 : SMT_GEMM_KTILE_64;
+}
+constexpr int kMaxKTile = 256;                // TMA box height limit
+static_assert(ktile_for(256) % 16 == 0 && ktile_for(128) % 16 == 0 && ktile_for(64) % 16 == 0, "K tile");
+static_assert(ktile_for(256) <= kMaxKTile && ktile_for(128) <= kMaxKTile && ktile_for(64) <= kMaxKTile, "K tile");
 #ifndef SMT_GEMM_EPI_WARPS
 #define SMT_GEMM_EPI_WARPS 8                  // multiple of 4 (one TMEM lane quarter per warp % 4)
 #endif
 constexpr int kEpiWarps = SMT_GEMM_EPI_WARPS;
 constexpr int kGemmThreads = 64 + 32 * kEpiWarps;   // warp 0 TMA, warp 1 MMA + TMEM alloc, warps 2-9 epilogue
 constexpr int kSmemBudget = 200 * 1024;       // pipeline stages (dynamic smem), leaves room for barriers
-constexpr int kMinKTilesPerSplit = 4 * 64 / kKTile;   // at least 256 tokens per split
+constexpr int kMinTokensPerSplit = 256;
 constexpr int kStageRow = 36;                 // floats per row of the epilogue transpose buffer (32 + 4 pad)
 constexpr size_t kCounterBytes = 16384;       // head of the workspace: self-resetting split-K arrival counters
 
 template <int B, int MH_>
 struct Cfg {
   static constexpr int MH = MH_;                              // M=128 accumulators per CTA
+  static constexpr int KT = ktile_for(B);                     // tokens per pipeline stage
+  static constexpr int CHUNK_BYTES = KT * 128;                // one {64 features x KT tokens} TMA box of 16-bit data
   static constexpr int A_LOAD = B >= 128 ? 2 * MH : 1;        // dy chunks fetched per stage
-  static constexpr int A_SLOTS = A_LOAD < 2 ? 2 : A_LOAD;     // an M=128 MMA always spans two chunks
+  // An M=128 MMA always spans two 64-row chunks.  For b = 64 only the first is loaded; with SMT_GEMM_B64_ALIAS the
+  // second half of the operand aliases the x chunk that follows it in the stage (initialised shared memory; it
+  // feeds accumulator rows 64..127, which are never read) instead of owning a slot.
+  static constexpr int A_SLOTS = (A_LOAD < 2 && !SMT_GEMM_B64_ALIAS) ? 2 : A_LOAD;
   static constexpr int B_LOAD = B / 64;                       // N = B
   static constexpr int TILES_PER_BLOCK = (B == 256 && MH == 1) ? 2 : 1;
   static constexpr int TILE_ROWS = B >= 128 ? 128 * MH : B;   // output rows one CTA produces
   static constexpr int TILE_ELEMS = TILE_ROWS * B;
-  static constexpr int STAGE_BYTES = (A_SLOTS + B_LOAD) * kChunkBytes;
+  static constexpr int STAGE_BYTES = (A_SLOTS + B_LOAD) * CHUNK_BYTES;
   static constexpr int STAGES_RAW = kSmemBudget / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > SMT_GEMM_MAX_STAGES ? SMT_GEMM_MAX_STAGES : STAGES_RAW;
 #ifdef SMT_GEMM_EXPERIMENT_SKIP_CHUNKS   // perf-only experiment (wrong results): skip that many A chunks per stage
@@ -69,7 +91,7 @@ struct Cfg {
 #else
   static constexpr int A_ISSUE = A_LOAD;
 #endif
-  static constexpr int TX_BYTES = (A_ISSUE + B_LOAD) * kChunkBytes;
+  static constexpr int TX_BYTES = (A_ISSUE + B_LOAD) * CHUNK_BYTES;
   static constexpr int TMEM_COLS = MH * B < 32 ? 32 : MH * B;  // 512 / 256 / 128 / 64 (powers of two)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024;  // + alignment slack
   static_assert(STAGES * STAGE_BYTES >= kEpiWarps * 32 * kStageRow * 4, "epilogue staging must fit in the pipeline smem");
@@ -225,7 +247,7 @@ struct GemmParams {
   int* counters;                  // fused reduction: 2 self-resetting ints per tile (NULL = separate reduce kernel)
   unsigned long long* trace;      // debug (SMT_GEMM_TRACE=1): 8 globaltimer stamps per CTA, else NULL
   int splits;
-  int kt_total;                   // number of K tiles = ceil(T / kKTile)
+  int kt_total;                   // number of K tiles = ceil(T / ktile_for(block))
   int kt_per_split;
   int out_dtype;                  // of G; the workspace is always fp32
   int accumulate;
@@ -348,7 +370,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) block_grad_umma_kernel(
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   auto a_addr = [&](int stage) { return smem_base + stage * C::STAGE_BYTES; };
-  auto b_addr = [&](int stage) { return smem_base + stage * C::STAGE_BYTES + C::A_SLOTS * kChunkBytes; };
+  auto b_addr = [&](int stage) { return smem_base + stage * C::STAGE_BYTES + C::A_SLOTS * C::CHUNK_BYTES; };
 
   int row, col;
   const CUtensorMap* map_x = &tmap_x;
@@ -395,21 +417,21 @@ __global__ void __launch_bounds__(kGemmThreads, 1) block_grad_umma_kernel(
         mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
         const uint32_t fb = smem_u32(&full_bar[stage]);
         mbar_expect_tx(fb, C::TX_BYTES);
-        const int t0 = (kt_begin + it) * kKTile;
+        const int t0 = (kt_begin + it) * C::KT;
         if (PAIR) {                      // my half of the shared dy strip, delivered to both CTAs
 #pragma unroll
           for (int c = 0; c < C::A_LOAD / 2; ++c) {
             const int cc = (int)pair_rank * (C::A_LOAD / 2) + c;
-            tma_load_2d_multicast(a_addr(stage) + cc * kChunkBytes, map_dy, fb, a_col0 + cc * 64, t0, (uint16_t)0x3);
+            tma_load_2d_multicast(a_addr(stage) + cc * C::CHUNK_BYTES, map_dy, fb, a_col0 + cc * 64, t0, (uint16_t)0x3);
           }
         } else {
 #pragma unroll
           for (int c = 0; c < C::A_ISSUE; ++c)
-            tma_load_2d(a_addr(stage) + c * kChunkBytes, map_dy, fb, a_col0 + c * 64, t0);
+            tma_load_2d(a_addr(stage) + c * C::CHUNK_BYTES, map_dy, fb, a_col0 + c * 64, t0);
         }
 #pragma unroll
         for (int c = 0; c < C::B_LOAD; ++c)
-          tma_load_2d(b_addr(stage) + c * kChunkBytes, map_x, fb, col * B + c * 64, t0);
+          tma_load_2d(b_addr(stage) + c * C::CHUNK_BYTES, map_x, fb, col * B + c * 64, t0);
       }
     }
   } else if (warp == 1) {
@@ -423,13 +445,13 @@ __global__ void __launch_bounds__(kGemmThreads, 1) block_grad_umma_kernel(
         tc_fence_after();
         if (it == 0) SMT_TRACE(2);                          // first operands landed
 #pragma unroll
-        for (int k = 0; k < kKTile / 16; ++k) {
+        for (int k = 0; k < C::KT / 16; ++k) {
           // 16 tokens = two 8-row swizzle atoms = 2048 B further down every chunk
-          const uint64_t bdesc = make_desc_mn_sw128(b_addr(stage) + k * 2048, kChunkBytes, 1024);
+          const uint64_t bdesc = make_desc_mn_sw128(b_addr(stage) + k * 2048, C::CHUNK_BYTES, 1024);
 #pragma unroll
           for (int mh = 0; mh < MH; ++mh) {
             const uint64_t adesc =
-                make_desc_mn_sw128(a_addr(stage) + mh * 2 * kChunkBytes + k * 2048, kChunkBytes, 1024);
+                make_desc_mn_sw128(a_addr(stage) + mh * 2 * C::CHUNK_BYTES + k * 2048, C::CHUNK_BYTES, 1024);
             umma_f16(tmem_base + mh * B, adesc, bdesc, idesc, (it > 0 || k > 0) ? 1u : 0u);
           }
         }
@@ -657,13 +679,14 @@ int env_int(const char* name, int dflt) {
 //
 // fitted on B200 over tools/sweep_plan.py (profiles/r01_plan_sweep_raw.txt; typical error < 8 %).  c_kt is the
 // measured time per 64-token K tile: 0.64 us for a whole 256-block per CTA (two M=128 UMMAs per K step, 84 % of the
-// UMMA issue rate), 0.41 us for a half block, 0.30 us for b = 128 / 64 (latency-bound pipeline).  Splitting K costs a
+// UMMA issue rate), 0.41 us for a half block, 0.27 / 0.22 us for b = 128 / 64 with their taller stages.  Splitting K costs a
 // second (reduce) kernel plus writing and re-reading the fp32 partial tiles, so small launches prefer half-block
 // tiles (half the partial bytes for the same CTA count) and one wave of CTAs.
 Plan make_plan(int n_blocks, int block, int64_t T) {
   const int sms = sm_count();
   Plan best{};
-  const int kt_total = (int)((T + kKTile - 1) / kKTile);
+  const int ktile = ktile_for(block);
+  const int kt_total = (int)((T + ktile - 1) / ktile);
   double best_cost = 1e30;
   const int force_mh = env_int("SMT_GEMM_FORCE_MH", 0), force_splits = env_int("SMT_GEMM_FORCE_SPLITS", 0);
   for (int mh = 1; mh <= (block == 256 ? 2 : 1); ++mh) {
@@ -672,8 +695,9 @@ Plan make_plan(int n_blocks, int block, int64_t T) {
     const int tiles = n_blocks * tpb;
     const int tile_rows = block >= 128 ? 128 * mh : block;
     const double tile_bytes = 4.0 * tile_rows * block;                 // fp32 tile
-    const double c_kt = (block == 256 ? (mh == 2 ? 0.64 : 0.41) : 0.30) * kKTile / 64.0;   // fitted per 64 tokens
-    int max_splits = kt_total / kMinKTilesPerSplit;
+    // fitted per 64 tokens (b = 128 / 64: with 128-token stages)
+    const double c_kt = (block == 256 ? (mh == 2 ? 0.64 : 0.41) : block == 128 ? 0.27 : 0.22) * ktile / 64.0;
+    int max_splits = (int)(T / kMinTokensPerSplit);
     if (max_splits < 1) max_splits = 1;
     if (max_splits > 64) max_splits = 64;
     for (int s = 1; s <= max_splits; ++s) {
@@ -713,8 +737,9 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D map over a row-major [T, features] 16-bit matrix; box = {64 features, kKTile tokens}, 128B swizzle.
-int encode_operand_map(CUtensorMap* map, const void* base, int64_t features, int64_t T, int64_t ld, int in_dtype) {
+// 2-D map over a row-major [T, features] 16-bit matrix; box = {64 features, ktile tokens}, 128B swizzle.
+int encode_operand_map(CUtensorMap* map, const void* base, int64_t features, int64_t T, int64_t ld, int in_dtype,
+                       int ktile) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) {
     set_error("smt_block_grad_gemm: cuTensorMapEncodeTiled not available from the driver");
@@ -722,7 +747,7 @@ int encode_operand_map(CUtensorMap* map, const void* base, int64_t features, int
   }
   const cuuint64_t gdim[2] = {(cuuint64_t)features, (cuuint64_t)T};
   const cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
-  const cuuint32_t box[2] = {64, (cuuint32_t)kKTile};
+  const cuuint32_t box[2] = {64, (cuuint32_t)ktile};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, in_dtype == SMT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
                    const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -902,7 +927,7 @@ extern "C" SMT_API int smt_block_grad_gemm(const void* x, int64_t ldx, int in_fe
     return SMT_OK;
   }
 
-  SMT_CHECK_ARG(T < (1ll << 31) - kKTile, "smt_block_grad_gemm: T too large");
+  SMT_CHECK_ARG(T < (1ll << 31) - kMaxKTile, "smt_block_grad_gemm: T too large");
   const Plan pl = make_plan(n_blocks, block, T);
   const size_t need = plan_workspace_bytes(pl);
   if (need > 0 && (workspace == nullptr || workspace_bytes < need)) {
@@ -912,8 +937,8 @@ extern "C" SMT_API int smt_block_grad_gemm(const void* x, int64_t ldx, int in_fe
   if (need > 0) SMT_CHECK_ARG(aligned16(workspace), "smt_block_grad_gemm: workspace must be 16-byte aligned");
 
   CUtensorMap mx, mdy;
-  if (int rc = encode_operand_map(&mx, x, in_features, T, ldx, in_dtype)) return rc;
-  if (int rc = encode_operand_map(&mdy, dy, out_features, T, lddy, in_dtype)) return rc;
+  if (int rc = encode_operand_map(&mx, x, in_features, T, ldx, in_dtype, ktile_for(block))) return rc;
+  if (int rc = encode_operand_map(&mdy, dy, out_features, T, lddy, in_dtype, ktile_for(block))) return rc;
 
   GemmParams gp{};
   gp.block_rc = block_rc;
@@ -948,21 +973,22 @@ extern "C" SMT_API int smt_debug_set_gemm_trace(void* dev_buf, int max_ctas) {
 }
 
 extern "C" SMT_API int smt_encode_operand_map(void* map_host, const void* base, int64_t features, int64_t T,
-                                              int64_t ld, int dtype) {
+                                              int64_t ld, int dtype, int block) {
+  SMT_CHECK_ARG(block_ok(block), "smt_encode_operand_map: block size %d not in {64,128,256}", block);
   SMT_CHECK_ARG(map_host && base, "smt_encode_operand_map: null pointer");
   SMT_CHECK_ARG(dtype == SMT_BF16 || dtype == SMT_F16, "smt_encode_operand_map: 16-bit operands only");
   SMT_CHECK_ARG((reinterpret_cast<uintptr_t>(map_host) & 63u) == 0, "smt_encode_operand_map: map must be 64-byte aligned");
   SMT_CHECK_ARG(features > 0 && T > 0 && ld >= features && (ld * 2) % 16 == 0 && aligned16(base),
                 "smt_encode_operand_map: bad operand geometry");
   static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap is 128 bytes");
-  return encode_operand_map(reinterpret_cast<CUtensorMap*>(map_host), base, features, T, ld, dtype);
+  return encode_operand_map(reinterpret_cast<CUtensorMap*>(map_host), base, features, T, ld, dtype, ktile_for(block));
 }
 
 namespace {
 // Row-sharing pairs (the first n_paired items) can take the 2-CTA multicast kernel when the launch is big enough to
-// need no split-K (whole-block tiles).  OPT-IN (SMT_GEMM_PAIRS=1): measured on B200 the multicast saves no time -- the
-// main loop is bound by the per-SM shared-memory fill, which multicast does not reduce -- and the second launch costs
-// ~85 us in bench.py (profiles/r01_kernels.md, "multicast pairs").  By default every item goes through the planner.
+// need no split-K (whole-block tiles).  OPT-IN (SMT_GEMM_PAIRS=1): measured on B200 the multicast saves no time (a
+// cluster of 2 does not reduce the L2 -> SM traffic) and the second launch costs ~85 us in bench.py
+// (profiles/r01_kernels.md section 1b).  By default every item goes through the planner.
 bool use_pairs(int n_items, int n_paired, int block, int64_t T) {
   if (block != 256 || n_paired < 2 || (n_paired & 1) || n_paired > n_items || !env_int("SMT_GEMM_PAIRS", 0)) return false;
   const Plan pl = make_plan(n_items, block, T);
@@ -992,7 +1018,7 @@ extern "C" SMT_API int smt_block_grad_gemm_grouped(const void* maps, const smt_g
                 "smt_block_grad_gemm_grouped: bad dtype");
   SMT_CHECK_ARG((reinterpret_cast<uintptr_t>(maps) & 63u) == 0 && aligned16(out_base),
                 "smt_block_grad_gemm_grouped: maps must be 64-byte and out_base 16-byte aligned");
-  SMT_CHECK_ARG(T < (1ll << 31) - kKTile, "smt_block_grad_gemm_grouped: T too large");
+  SMT_CHECK_ARG(T < (1ll << 31) - kMaxKTile, "smt_block_grad_gemm_grouped: T too large");
   SMT_CHECK_ARG(n_paired <= n_items && (n_paired & 1) == 0, "smt_block_grad_gemm_grouped: n_paired must be even and <= n_items");
   const size_t need_total = smt_block_grad_gemm_grouped_workspace_bytes(n_items, n_paired, block, T);
   if (need_total > 0 && (workspace == nullptr || workspace_bytes < need_total)) {
@@ -1007,7 +1033,7 @@ extern "C" SMT_API int smt_block_grad_gemm_grouped(const void* maps, const smt_g
   gp.out_dtype = out_dtype;
   gp.accumulate = accumulate;
   gp.in_fmt = in_dtype == SMT_BF16 ? 1 : 0;
-  gp.kt_total = (int)((T + kKTile - 1) / kKTile);
+  gp.kt_total = (int)((T + ktile_for(block) - 1) / ktile_for(block));
 
   int first_single = 0;
   if (use_pairs(n_items, n_paired, block, T)) {

@@ -459,8 +459,8 @@ class BlockGradBatch:
         host = stage.numpy()
         in_id = dtype_id(in_dt)
         for _key, (i, t) in maps.items():
-            check(lib.smt_encode_operand_map(stage.data_ptr() + i * 128, t.data_ptr(), t.shape[1], T, t.stride(0), in_id),
-                  "smt_encode_operand_map")
+            check(lib.smt_encode_operand_map(stage.data_ptr() + i * 128, t.data_ptr(), t.shape[1], T, t.stride(0),
+                                             in_id, block), "smt_encode_operand_map")
         host[n_maps * 128:].view(item_dt)[:] = np.array(items, dtype=item_dt)
         dev_buf = stage.to(dev, non_blocking=True)
         ws_bytes = lib.smt_block_grad_gemm_grouped_workspace_bytes(n_items, n_paired, block, T)
