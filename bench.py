@@ -385,13 +385,16 @@ def run_ours(args):
     traffic = None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "r01_bench_gemm_traffic.json")))
-        if args.layers == 32 and not args.no_group and world == 1 and n_mlp == 0 and args.attn_ratio == ATTN_RATIO:
+        if args.layers == 32 and not args.no_group and world == 1 and n_mlp == 0 and args.attn_ratio == ATTN_RATIO \
+                and os.environ.get("SMT_GEMM_2SM") != "0":
             traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
     except Exception:
         pass
     adam_ms = statistics.mean(ms for ms, _ in adam_t) if adam_t else None
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    roofline = {"kernel": "block_grad_umma_kernel<256> (+ splitk_reduce)", "bound": "tensor", "achieved": achieved,
+    gemm_kernel = "block_grad_umma_kernel<256, 2, grouped> (single-CTA tiles)" if os.environ.get("SMT_GEMM_2SM") == "0" \
+        else "block_grad_umma_2sm_kernel (cta_group::2, two 256x256 blocks per SM pair)"
+    roofline = {"kernel": gemm_kernel, "bound": "tensor", "achieved": achieved,
                 "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
                 "traffic_note": "dram read+write bytes per launch from one ncu --set full capture of this workload "
                                 "(profiles/r01_bench_gemm_traffic.json); algorithmic minimum in min_hbm_bytes_per_launch",

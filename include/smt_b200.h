@@ -158,10 +158,10 @@ SMT_API int smt_block_grad_gemm(const void* x, int64_t ldx, int in_features,
  * (`out_off` = element offset from `out_base`, a multiple of 8).  Same arithmetic and determinism as the
  * single-problem call.
  * Row-sharing pairs: the first `n_paired` items (an even number, 0 = none) must come as consecutive pairs that have
- * the same `map_dy` and the same `row`.  With SMT_GEMM_PAIRS=1 in the environment and a launch large enough to need
- * no split-K (b = 256), those pairs run as 2-CTA clusters that fetch the shared dy strip once and TMA-multicast it to
- * both CTAs (bit-identical results; measured no faster on B200, hence opt-in).  Otherwise the pairing is only an
- * ordering hint: row-sharing tiles sit next to each other in the grid, so the shared strip is an L2 hit. */
+ * the same `map_dy` and the same `row`.  A launch of b = 256 blocks large enough to need no split-K runs on SM pairs
+ * (tcgen05 cta_group::2): items (2c, 2c+1) go to CTA pair c, which loads the dy strip once when the two items share
+ * it.  SMT_GEMM_2SM=0 in the environment selects the single-CTA kernel (bit-identical results), where the pairing is
+ * only an ordering hint, and SMT_GEMM_PAIRS=1 then runs the pairs as cta_group::1 clusters with TMA multicast. */
 typedef struct smt_gemm_item {
   uint32_t map_dy;   /* index into maps: descriptor of the dy operand   */
   uint32_t map_x;    /* index into maps: descriptor of the x operand    */

@@ -547,6 +547,190 @@ __global__ void __launch_bounds__(kGemmThreads, 1) block_grad_umma_kernel(
   }
 }
 
+// ---- 2-SM (cta_group::2) kernel: two whole b = 256 blocks per CTA pair ---------------------------------
+//
+// A cluster of two CTAs (one SM pair) works on TWO grouped work items.  Every UMMA is a `cta_group::2` instruction with
+// M = 256 (CTA r owns dy rows [128 r, 128 r + 128) of the block and accumulator lanes for those rows) and N = 256 whose
+// x operand is SPLIT across the pair (CTA r loads x columns [128 r, 128 r + 128) of the block): per 64-token stage a CTA
+// fills  A0 (16 KiB) + B0 half (16 KiB) + A1 (16 KiB) + B1 half (16 KiB) = 64 KiB for the same UMMA work per SM as the
+// single-CTA whole-block tile -- and only 48 KiB (4 instead of 3 stages) when the two items share their dy strip
+// (same operand, same block row: the first `n_paired` items of a grouped launch), because A1 == A0 is then not
+// loaded at all.  Fewer TMA boxes and bytes per unit of tensor work is what the single-CTA tile is short of
+// (profiles/r01_kernels.md section 1b).
+// Protocol (the CUTLASS sm100 2-SM scheme): both CTAs run a TMA producer that loads ITS halves with
+// `cp.async.bulk.tensor...cta_group::2` signalling the LEADER's (cluster rank 0) full barrier, which expects the bytes
+// of both CTAs; only the leader issues UMMAs; stage-free and accumulators-ready commits are multicast to both CTAs.
+
+constexpr int k2smStageChunks = 8;                                   // A0, B0, A1, B1: two 64-feature chunks each
+constexpr int k2smKTile = ktile_for(256);
+constexpr int k2smChunkBytes = k2smKTile * 128;
+constexpr int k2smMaxStages = 4;
+constexpr int k2smSmemBytes = 3 * k2smStageChunks * k2smChunkBytes + 1024;   // 3 x 64 KiB = 4 x 48 KiB
+
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t slot_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_commit_multicast(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
+// TMA load into THIS CTA's shared memory whose completion bytes go to the barrier at the same offset in the pair's
+// even (leader) CTA: bit 24 of a shared::cluster address is the CTA's rank within the pair.
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 1) block_grad_umma_2sm_kernel(const GemmParams p, int n_items) {
+  constexpr int B = 256, KT = k2smKTile, CB = k2smChunkBytes;
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[k2smMaxStages];
+  __shared__ __align__(8) uint64_t empty_bar[k2smMaxStages];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();               // 0 = leader (issues the UMMAs)
+  const int pair = blockIdx.x >> 1;
+  const smt_gemm_item it0 = p.items[2 * pair];
+  const bool has2 = 2 * pair + 1 < n_items;
+  const smt_gemm_item it1 = has2 ? p.items[2 * pair + 1] : it0;
+  const bool shared_a = has2 && it1.map_dy == it0.map_dy && it1.row == it0.row;
+  // stage layout: [A0 | B0 | B1] (shared dy strip, 48 KiB, 4 stages) or [A0 | B0 | A1 | B1] (64 KiB, 3 stages)
+  const int stage_bytes = (shared_a ? 6 : 8) * CB;
+  const int n_stages = shared_a ? 4 : 3;
+  const uint32_t off_b0 = 2 * CB, off_a1 = 4 * CB, off_b1 = shared_a ? 4 * CB : 6 * CB;
+  const uint32_t my_bytes = (uint32_t)((has2 ? (shared_a ? 6 : 8) : 4) * CB);
+  const int n_kt = p.kt_total;
+
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(p.maps + it0.map_x);
+    prefetch_tmap(p.maps + it0.map_dy);
+    for (int s = 0; s < k2smMaxStages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(&tmem_full_bar), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2sm(smem_u32(&tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                  // both CTAs' barriers and TMEM exist before anything crosses the pair
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs): my 128 dy rows and my 128 x columns of each block =====
+    if (lane == 0) {
+      const CUtensorMap* mdy0 = p.maps + it0.map_dy;
+      const CUtensorMap* mx0 = p.maps + it0.map_x;
+      const CUtensorMap* mdy1 = p.maps + it1.map_dy;
+      const CUtensorMap* mx1 = p.maps + it1.map_x;
+      const int a0 = it0.row * B + (int)rank * 128, b0 = it0.col * B + (int)rank * 128;
+      const int a1 = it1.row * B + (int)rank * 128, b1 = it1.col * B + (int)rank * 128;
+      for (int it = 0; it < n_kt; ++it) {
+        const int stage = it % n_stages;
+        const uint32_t phase = (uint32_t)(it / n_stages) & 1u;
+        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1u);
+        const uint32_t fb = smem_u32(&full_bar[stage]);
+        if (rank == 0) mbar_expect_tx(fb, 2u * my_bytes);          // the leader's barrier counts both CTAs' bytes
+        const uint32_t st = smem_base + (uint32_t)(stage * stage_bytes);
+        const int t0 = it * KT;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          tma_load_2d_2sm(st + c * CB, mdy0, fb, a0 + c * 64, t0);
+          tma_load_2d_2sm(st + off_b0 + c * CB, mx0, fb, b0 + c * 64, t0);
+        }
+        if (has2) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            if (!shared_a) tma_load_2d_2sm(st + off_a1 + c * CB, mdy1, fb, a1 + c * 64, t0);
+            tma_load_2d_2sm(st + off_b1 + c * CB, mx1, fb, b1 + c * 64, t0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== UMMA issuer: one thread of the leader CTA, on behalf of both SMs =====
+    if (lane == 0 && rank == 0) {
+      const uint32_t idesc = make_idesc(p.in_fmt, 256, B);
+      for (int it = 0; it < n_kt; ++it) {
+        const int stage = it % n_stages;
+        const uint32_t phase = (uint32_t)(it / n_stages) & 1u;
+        mbar_wait(smem_u32(&full_bar[stage]), phase);
+        tc_fence_after();
+        const uint32_t st = smem_base + (uint32_t)(stage * stage_bytes);
+#pragma unroll
+        for (int k = 0; k < KT / 16; ++k) {
+          const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
+          const uint64_t a0d = make_desc_mn_sw128(st + k * 2048, CB, 1024);
+          umma2_f16(tmem_base, a0d, make_desc_mn_sw128(st + off_b0 + k * 2048, CB, 1024), idesc, acc);
+          if (has2) {
+            const uint64_t a1d = shared_a ? a0d : make_desc_mn_sw128(st + off_a1 + k * 2048, CB, 1024);
+            umma2_f16(tmem_base + B, a1d, make_desc_mn_sw128(st + off_b1 + k * 2048, CB, 1024), idesc, acc);
+          }
+        }
+        umma2_commit_multicast(smem_u32(&empty_bar[stage]), (uint16_t)0x3);   // frees the stage in both CTAs
+      }
+      umma2_commit_multicast(smem_u32(&tmem_full_bar), (uint16_t)0x3);        // accumulators complete, both CTAs
+    }
+  } else {
+    // ===== epilogue (both CTAs): my 128 rows of each block =====
+    const int ew = warp - 2, q = warp & 3, par = ew >> 2;
+    mbar_wait(smem_u32(&tmem_full_bar), 0);
+    tc_fence_after();
+    float* stage = reinterpret_cast<float*>(smem_gen) + ew * 32 * kStageRow;   // pipeline buffers are dead by now
+#pragma unroll 1
+    for (int blk = 0; blk < (has2 ? 2 : 1); ++blk) {
+      const int64_t out0 = (blk == 0 ? it0.out_off : it1.out_off) + (int64_t)((int)rank * 128 + q * 32) * B;
+#pragma unroll 1
+      for (int cc = par; cc < B / 32; cc += kEpiWarps / 4) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(blk * B + cc * 32), r);
+        tmem_ld_wait();
+        const int64_t off = out0 + cc * 32;
+        if (p.out_dtype == SMT_F32) {
+          if (p.accumulate) store_subtile<SMT_F32, true>(stage, r, lane, p.out, off, B);
+          else store_subtile<SMT_F32, false>(stage, r, lane, p.out, off, B);
+        } else if (p.out_dtype == SMT_BF16) {
+          if (p.accumulate) store_subtile<SMT_BF16, true>(stage, r, lane, p.out, off, B);
+          else store_subtile<SMT_BF16, false>(stage, r, lane, p.out, off, B);
+        } else {
+          if (p.accumulate) store_subtile<SMT_F16, true>(stage, r, lane, p.out, off, B);
+          else store_subtile<SMT_F16, false>(stage, r, lane, p.out, off, B);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                  // nobody leaves (or frees TMEM) while the pair may still touch it
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
 // ---- split-K reduction: G = sum_s partial[s] (fixed order) -----------------------------------------
 
 template <int ODT>
@@ -811,6 +995,26 @@ int launch_umma_pairs(const GemmParams& gp, int n_paired, cudaStream_t st) {
   return SMT_OK;
 }
 
+// Two whole blocks per CTA pair, cta_group::2 UMMAs (grouped launches of b = 256 blocks that need no split-K).
+int launch_umma_2sm(const GemmParams& gp, int n_items, cudaStream_t st) {
+  SMT_CHECK_CUDA(cudaFuncSetAttribute(block_grad_umma_2sm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      k2smSmemBytes));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(2 * ((n_items + 1) / 2)));
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = k2smSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  SMT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, block_grad_umma_2sm_kernel, gp, n_items));
+  return SMT_OK;
+}
+
 // split-K reduce, launched with programmatic stream serialization so that its launch overlaps the GEMM
 int launch_reduce(const float* ws, void* out, const smt_gemm_item* items, int block, const Plan& pl, int n_blocks,
                   int out_dtype, int accumulate, cudaStream_t st) {
@@ -996,6 +1200,17 @@ bool use_pairs(int n_items, int n_paired, int block, int64_t T) {
 }
 }  // namespace
 
+namespace {
+// Large grouped launches of b = 256 blocks (no split-K, whole-block tiles) run on SM pairs (cta_group::2): bit-identical
+// to the single-CTA kernel and 3-5 % faster alone / ~1 % in bench.py (profiles/r01_kernels.md section 1b).
+// SMT_GEMM_2SM=0 switches back to the single-CTA kernel.
+bool use_2sm(int n_items, int block, int64_t T) {
+  if (block != 256 || n_items < 2 || !env_int("SMT_GEMM_2SM", 1)) return false;
+  const Plan pl = make_plan(n_items, block, T);
+  return pl.splits == 1 && pl.mh == 2;
+}
+}  // namespace
+
 extern "C" SMT_API size_t smt_block_grad_gemm_grouped_workspace_bytes(int n_items, int n_paired, int block, int64_t T) {
   if (n_items <= 0 || T <= 0 || !block_ok(block)) return 0;
   size_t need = plan_workspace_bytes(make_plan(n_items, block, T));
@@ -1035,6 +1250,14 @@ extern "C" SMT_API int smt_block_grad_gemm_grouped(const void* maps, const smt_g
   gp.in_fmt = in_dtype == SMT_BF16 ? 1 : 0;
   gp.kt_total = (int)((T + ktile_for(block) - 1) / ktile_for(block));
 
+  if (use_2sm(n_items, block, T)) {
+    gp.items = items;
+    gp.splits = 1;
+    gp.kt_per_split = gp.kt_total;
+    if (int rc = launch_umma_2sm(gp, n_items, st)) return rc;
+    set_launch_count(1);
+    return SMT_OK;
+  }
   int first_single = 0;
   if (use_pairs(n_items, n_paired, block, T)) {
     gp.items = items;

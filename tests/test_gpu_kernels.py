@@ -409,7 +409,8 @@ def test_grouped_gemm_row_sharing_pairs_multicast(ops, monkeypatch):
         assert batch.flush(accumulate=False) == 1
         return out
 
-    monkeypatch.setenv("SMT_GEMM_PAIRS", "1")                      # opt-in: the default is the single-CTA kernel
+    monkeypatch.setenv("SMT_GEMM_2SM", "0")                        # compare the two cta_group::1 variants
+    monkeypatch.setenv("SMT_GEMM_PAIRS", "1")                      # opt-in multicast clusters
     launches0 = ops.LAUNCHES["total"]
     paired = run()
     assert ops.LAUNCHES["total"] - launches0 == 2                  # pair clusters + the left-over singles
@@ -423,3 +424,49 @@ def test_grouped_gemm_row_sharing_pairs_multicast(ops, monkeypatch):
         got = paired[i * n * b * b:(i + 1) * n * b * b].view(n, b, b)
         want = torch.stack([ref[r * b:(r + 1) * b, c * b:(c + 1) * b] for r, c in idx])
         assert (got - want).abs().max().item() <= 2e-5 * want.abs().max().item()
+
+
+@pytest.mark.parametrize("out_dtype,accumulate", [(torch.float32, False), (torch.bfloat16, True)])
+def test_grouped_gemm_2sm_cta_pairs(ops, monkeypatch, out_dtype, accumulate):
+    """cta_group::2 kernel (the default for large grouped b = 256 launches; SMT_GEMM_2SM=0 = single-CTA kernel): two
+    blocks per SM pair, x operand split across the pair, dy strip loaded once when the two blocks share their block
+    row.  Row-sharing pairs, unrelated pairs, an odd tail and a ragged token count; must match the single-CTA kernel
+    (same K order => bit-identical) and the dense reference."""
+    torch.manual_seed(11)
+    T, b = 1000, 256                                                    # 1000 = 15 full 64-token stages + 40
+    P = 5
+    xs = [torch.randn(T, 1536, device="cuda").bfloat16() for _ in range(P)]
+    dys = [torch.randn(T, 2048, device="cuda").bfloat16() for _ in range(P)]
+    idx = [(0, 4)] + [(1, c) for c in (0, 5)] + [(2, c) for c in (1, 2, 3)] + [(3, c) for c in (0, 1, 2, 4, 5)] + \
+          [(r, c) for r in (4, 5, 6, 7) for c in range(6)] + [(0, 1), (2, 5), (5, 0)]
+    idx = list(dict.fromkeys(idx))
+    uses = [idx[:-2]] + [idx] * (P - 1)                                 # odd total => one cluster with a single block
+    offs = [0]
+    for u in uses:
+        offs.append(offs[-1] + len(u) * b * b)
+    assert offs[-1] // (b * b) >= 148 and (offs[-1] // (b * b)) % 2 == 1
+    init = (torch.randn(offs[-1], device="cuda") * 3).to(out_dtype)
+
+    def run():
+        out = init.clone() if accumulate else torch.zeros(offs[-1], device="cuda", dtype=out_dtype)
+        batch = ops.BlockGradBatch()
+        for i in range(P):
+            batch.add(xs[i], dys[i], uses[i], out[offs[i]:offs[i + 1]].view(-1, b), b)
+        launches0 = ops.LAUNCHES["total"]
+        batch.flush(accumulate=accumulate)
+        return out, ops.LAUNCHES["total"] - launches0
+
+    monkeypatch.setenv("SMT_GEMM_2SM", "0")
+    single, _ = run()
+    monkeypatch.delenv("SMT_GEMM_2SM", raising=False)              # default: cta_group::2
+    paired, launches = run()
+    assert launches == 1
+    assert torch.equal(paired, single)
+    for i in range(P):
+        ref = dys[i].float().t() @ xs[i].float()
+        got = paired[offs[i]:offs[i + 1]].view(len(uses[i]), b, b).float()
+        want = torch.stack([ref[r * b:(r + 1) * b, c * b:(c + 1) * b] for r, c in uses[i]])
+        if accumulate:
+            want = want + init[offs[i]:offs[i + 1]].view(len(uses[i]), b, b).float()
+        tol = 2e-5 if out_dtype == torch.float32 else 2 ** -7
+        assert (got - want).abs().max().item() <= tol * want.abs().max().item()
