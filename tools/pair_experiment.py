@@ -55,6 +55,7 @@ for label, n_mod, rows, cols, per_row in (("k/v-like modules: 4x16 blocks, 8 per
         batch.flush(accumulate=False)
 
     fl = 2.0 * b * b * T * n
+    os.environ["SMT_GEMM_2SM"] = "0"
     os.environ["SMT_GEMM_PAIRS"] = "1"
     t_pair = timeit(run)
     os.environ.pop("SMT_GEMM_PAIRS", None)
