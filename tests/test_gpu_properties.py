@@ -127,3 +127,48 @@ def test_selection_at_llama_scale_matches_oracle_exactly(ops):
     assert list(got.items()) == list(want.items())
     got_dev = H.select_submatrix_based_on_grads({k: v.cuda() for k, v in grads.items()}, dims, n)
     assert list(got_dev.items()) == list(want.items())
+
+
+def test_grouped_launch_at_llama_scale_properties(ops):
+    """BASELINE config 3 shape: 869 blocks of 256 x 256 over 27 q/k/v-like modules, T = 8192 tokens, ONE grouped launch
+    (the cta_group::2 kernel).  Size-independent properties: run-to-run bit-identical, token additivity, exact sign
+    symmetry, equality with per-module launches (split-K plans differ => fp32 tolerance), spot checks vs torch fp32."""
+    torch.manual_seed(2)
+    T, b = 8192, 256
+    g = torch.Generator().manual_seed(5)
+    shapes = [(4096, 4096)] * 9 + [(1024, 4096)] * 18                 # (out, in): q-like and k/v-like
+    xs = [torch.randn(T, 4096, device="cuda").bfloat16() for _ in range(9)]            # q/k/v of a layer share x
+    mods, total = [], 0
+    for m, (fo, fi) in enumerate(shapes):
+        nb = (fo // b) * (fi // b)
+        n = 869 // 27 + (1 if m < 869 % 27 else 0)
+        perm = torch.randperm(nb, generator=g)[:n].tolist()
+        idx = [(p // (fi // b), p % (fi // b)) for p in perm]
+        dy = torch.randn(T, fo, device="cuda").bfloat16()
+        mods.append((xs[m % 9], dy, idx, total))
+        total += n * b * b
+    assert total == 869 * b * b
+
+    def run(t0, t1, sign=1.0):
+        out = torch.zeros(total, device="cuda")
+        batch = ops.BlockGradBatch()
+        for x, dy, idx, off in mods:
+            batch.add(x[t0:t1], dy[t0:t1] * sign, idx, out[off:off + len(idx) * b * b].view(-1, b), b)
+        assert batch.flush(accumulate=False) == 1
+        return out
+
+    G = run(0, T)
+    assert torch.equal(G, run(0, T))                                  # deterministic
+    assert torch.equal(run(0, T, -1.0), -G)                           # exact sign symmetry
+    scale = G.abs().max().item()
+    h = T // 2 + 192
+    assert (G - (run(0, h) + run(h, T))).abs().max().item() <= 2e-5 * scale      # additivity over tokens
+    for m in (0, 8, 9, 26):                                           # per-module launches (other split-K plans)
+        x, dy, idx, off = mods[m]
+        rc = ops.make_block_rc(idx, "cuda")
+        Gm = ops.block_grad_gemm(x, dy, rc, b, out_dtype=torch.float32)
+        assert (G[off:off + len(idx) * b * b].view(-1, b) - Gm).abs().max().item() <= 2e-5 * scale
+        r, c = idx[len(idx) // 2]
+        ref = dy[:, r * b:(r + 1) * b].float().t() @ x[:, c * b:(c + 1) * b].float()
+        i = len(idx) // 2
+        assert (Gm[i * b:(i + 1) * b] - ref).abs().max().item() <= 2e-5 * scale
