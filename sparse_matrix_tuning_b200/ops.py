@@ -6,6 +6,7 @@ Every function launches on the CURRENT CUDA stream of the tensors' device.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence, Tuple
 
 import torch
@@ -433,25 +434,35 @@ class BlockGradBatch:
 
         esize = prs[0][3].element_size()
         base_ptr = min(pr[3].data_ptr() for pr in prs)
-        entries = []
+        # Work-item order = execution order (CTAs / CTA pairs are dispatched in item order):
+        #   * within a module, blocks are walked by (block row, block column), and two consecutive blocks of one block
+        #     row form a PAIR: the cta_group::2 kernel gives items (2c, 2c+1) to CTA pair c and loads the shared dy strip
+        #     once, so every pair must start at an even position;
+        #   * a module's unpaired blocks follow its pairs immediately (their strips are still in L2), not at the end of
+        #     the launch; an odd one out is carried over to the next module to keep the even alignment.
+        legacy = os.environ.get("SMT_GEMM_PAIRS") == "1" and os.environ.get("SMT_GEMM_2SM") == "0"
+        items, carry, all_pairs, all_singles = [], [], [], []
         for x2d, dy2d, idx, out, _b in prs:
             mx, mdy = map_index(x2d), map_index(dy2d)
             off0 = (out.data_ptr() - base_ptr) // esize
-            # CTAs are scheduled in item order: keep blocks that share a dy strip (same block row) adjacent so that
-            # they run in the same wave and hit each other's lines in L2
-            for i, (r, c) in sorted(enumerate(idx), key=lambda t: (t[1][0], t[1][1])):
-                entries.append((mdy, mx, r, c, off0 + i * block * block))
-        # consecutive blocks of the same block row of the same dy operand form a pair and are placed first: adjacent
-        # tiles then share their dy strip through L2 (and, with SMT_GEMM_PAIRS=1, run as 2-CTA multicast clusters)
-        pairs, singles, i = [], [], 0
-        while i < len(entries):
-            if i + 1 < len(entries) and entries[i][0] == entries[i + 1][0] and entries[i][2] == entries[i + 1][2]:
-                pairs += [entries[i], entries[i + 1]]
-                i += 2
-            else:
-                singles.append(entries[i])
-                i += 1
-        items, n_paired = pairs + singles, len(pairs)
+            entries = [(mdy, mx, r, c, off0 + i * block * block)
+                       for i, (r, c) in sorted(enumerate(idx), key=lambda t: (t[1][0], t[1][1]))]
+            pairs, singles, i, n_carried = [], list(carry), 0, len(carry)
+            while i < len(entries):
+                if i + 1 < len(entries) and entries[i][2] == entries[i + 1][2]:
+                    pairs += [entries[i], entries[i + 1]]
+                    i += 2
+                else:
+                    singles.append(entries[i])
+                    i += 1
+            all_pairs += pairs
+            all_singles += singles[n_carried:]
+            carry = [singles.pop()] if len(singles) % 2 else []
+            items += pairs + singles
+        items += carry
+        n_paired = 0
+        if legacy:      # the opt-in cta_group::1 multicast variant wants all pairs as a prefix of the item list
+            items, n_paired = all_pairs + all_singles, len(all_pairs)
         n_items, n_maps = len(items), len(maps)
         item_dt = np.dtype([("map_dy", "<u4"), ("map_x", "<u4"), ("row", "<i4"), ("col", "<i4"), ("out_off", "<i8")])
         nbytes = n_maps * 128 + n_items * item_dt.itemsize
