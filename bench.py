@@ -415,6 +415,7 @@ def run_ours(args):
                                    + ("" if args.layers == 32 else f" [DEBUG: {args.layers} layers only]"),
                        "selected_blocks": n_blocks, "block": BLOCK, "trainable_elements": trainable,
                        "modules_with_blocks": len(sel), "grouped_block_grad_launch": not args.no_group,
+                       "grouped_launch_shape": dict(ops.LAST_GROUP),
                        "total_blocks_budget_base": total_blocks, "gradient_checkpointing": not args.no_ckpt,
                        "parallelism": f"dp{world}", "tokens_per_step_per_gpu": T,
                        "l2": "inputs larger than L2 (16 GB of weights streamed per step); no explicit flush",

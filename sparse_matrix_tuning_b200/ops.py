@@ -383,6 +383,9 @@ def compact_adam(master: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.
 
 # ---- grouped block-gradient GEMM: several (x, dy) problems in one launch ------------------------------------
 
+LAST_GROUP: dict = {}     # shape of the most recent grouped launch (bench.py reports it)
+
+
 class BlockGradBatch:
     """Collects block-gradient problems (one per module backward) and runs them as ONE grouped tcgen05 launch.
 
@@ -464,6 +467,8 @@ class BlockGradBatch:
         if legacy:      # the opt-in cta_group::1 multicast variant wants all pairs as a prefix of the item list
             items, n_paired = all_pairs + all_singles, len(all_pairs)
         n_items, n_maps = len(items), len(maps)
+        LAST_GROUP.update(items=n_items, operands=n_maps, row_sharing_pairs=sum(
+            1 for k in range(0, n_items - 1, 2) if items[k][0] == items[k + 1][0] and items[k][2] == items[k + 1][2]))
         item_dt = np.dtype([("map_dy", "<u4"), ("map_x", "<u4"), ("row", "<i4"), ("col", "<i4"), ("out_off", "<i8")])
         nbytes = n_maps * 128 + n_items * item_dt.itemsize
         stage = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
