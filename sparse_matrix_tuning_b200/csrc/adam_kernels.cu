@@ -32,32 +32,6 @@ __device__ __forceinline__ void load8(const void* p, int64_t vec, float (&g)[8])
   }
 }
 
-__device__ __forceinline__ void load8_rw(const float* p, int64_t vec, float (&g)[8]) {
-  const float4 a = reinterpret_cast<const float4*>(p)[2 * vec];
-  const float4 b = reinterpret_cast<const float4*>(p)[2 * vec + 1];
-  g[0] = a.x; g[1] = a.y; g[2] = a.z; g[3] = a.w;
-  g[4] = b.x; g[5] = b.y; g[6] = b.z; g[7] = b.w;
-}
-
-template <int ODT>
-__device__ __forceinline__ void store8(void* base, int64_t elem_off, const float (&p)[8]) {
-  if (ODT == SMT_F32) {
-    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + elem_off);
-    o[0] = make_float4(p[0], p[1], p[2], p[3]);
-    o[1] = make_float4(p[4], p[5], p[6], p[7]);
-  } else {
-    uint4 u;
-    if (ODT == SMT_BF16) {
-      u.x = pack_bf16x2(p[0], p[1]); u.y = pack_bf16x2(p[2], p[3]);
-      u.z = pack_bf16x2(p[4], p[5]); u.w = pack_bf16x2(p[6], p[7]);
-    } else {
-      u.x = pack_f16x2(p[0], p[1]); u.y = pack_f16x2(p[2], p[3]);
-      u.z = pack_f16x2(p[4], p[5]); u.w = pack_f16x2(p[6], p[7]);
-    }
-    *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(base) + elem_off) = u;
-  }
-}
-
 struct AdamArgs {
   float lr, beta1, beta2, eps, wd, bc1, bc2, grad_scale, max_norm;
 };
