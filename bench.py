@@ -421,7 +421,8 @@ def run_ours(args):
                        "l2": "inputs larger than L2 (16 GB of weights streamed per step); no explicit flush",
                        "per_gpu_value": value / world, "loss_last": last,
                        "tokens_per_s_without_checkpointing": (tokens / (ms_nockpt / 1e3)) if ms_nockpt else None,
-                       "warmup_path_ms": {"capture_one_backward": t_capture * 1e3, "scores_topk": t_select * 1e3}},
+                       # capture = the process's FIRST forward + backward (cold: library init, allocator growth) + block-sum accumulation
+                       "warmup_path_ms": {"capture_first_fwd_bwd_cold": t_capture * 1e3, "scores_topk": t_select * 1e3}},
             "e2e": {"value": e2e_value, "unit": "tokens/s", "h2d_bytes_per_step": B * S * 8, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline}
