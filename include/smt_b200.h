@@ -157,11 +157,10 @@ SMT_API int smt_block_grad_gemm(const void* x, int64_t ldx, int in_features,
  * array with one entry per block: which dy / x descriptor, which block (row, col), and where its b x b result goes
  * (`out_off` = element offset from `out_base`, a multiple of 8).  Same arithmetic and determinism as the
  * single-problem call.
- * Row-sharing pairs: the first `n_paired` items (an even number, 0 = none) must come as consecutive pairs that have
- * the same `map_dy` and the same `row`.  A launch of b = 256 blocks large enough to need no split-K runs on SM pairs
- * (tcgen05 cta_group::2): items (2c, 2c+1) go to CTA pair c, which loads the dy strip once when the two items share
- * it.  SMT_GEMM_2SM=0 in the environment selects the single-CTA kernel (bit-identical results), where the pairing is
- * only an ordering hint, and SMT_GEMM_PAIRS=1 then runs the pairs as cta_group::1 clusters with TMA multicast. */
+ * Item order is execution order.  A launch of b = 256 blocks large enough to need no split-K runs on SM pairs
+ * (tcgen05 cta_group::2): items (2c, 2c+1) go to CTA pair c, which loads the dy strip once when the two items have the
+ * same `map_dy` and `row` - so callers should place row-sharing blocks on such positions (ops.BlockGradBatch does).
+ * SMT_GEMM_2SM=0 in the environment selects the single-CTA kernel (bit-identical results). */
 typedef struct smt_gemm_item {
   uint32_t map_dy;   /* index into maps: descriptor of the dy operand   */
   uint32_t map_x;    /* index into maps: descriptor of the x operand    */
@@ -172,8 +171,8 @@ typedef struct smt_gemm_item {
 /* `block` = the block size of the launch the descriptor will be used in (it fixes the TMA box height). */
 SMT_API int smt_encode_operand_map(void* map_host, const void* base, int64_t features, int64_t T, int64_t ld,
                                    int dtype, int block);
-SMT_API size_t smt_block_grad_gemm_grouped_workspace_bytes(int n_items, int n_paired, int block, int64_t T);
-SMT_API int smt_block_grad_gemm_grouped(const void* maps, const smt_gemm_item* items, int n_items, int n_paired,
+SMT_API size_t smt_block_grad_gemm_grouped_workspace_bytes(int n_items, int block, int64_t T);
+SMT_API int smt_block_grad_gemm_grouped(const void* maps, const smt_gemm_item* items, int n_items,
                                         int64_t T, int block, int in_dtype, void* out_base, int out_dtype,
                                         int accumulate, void* workspace, size_t workspace_bytes, void* stream);
 /* debug: register a device buffer of 8*max_ctas uint64; each CTA of smt_block_grad_gemm stamps %globaltimer at its

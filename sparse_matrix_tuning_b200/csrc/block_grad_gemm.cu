@@ -141,15 +141,6 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
-// same, delivered to every CTA of the cluster named in `mask` (same CTA-relative smem offset and mbarrier offset)
-__device__ __forceinline__ void tma_load_2d_multicast(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
-                                                      int c1, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%4, %5}], [%2], %3;"
-      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "h"(mask), "r"(c0), "r"(c1)
-      : "memory");
-}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -188,11 +179,6 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 // arrive on an mbarrier once every previously issued tcgen05.mma has completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// same, arriving on the barrier at this CTA-relative offset in every CTA of the cluster named in `mask`
-__device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(bar), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -341,13 +327,7 @@ __device__ __forceinline__ void fused_reduce_slice(const float* __restrict__ par
   }
 }
 
-// PAIR: launched as clusters of two CTAs whose blocks lie in the same block row of the same dy operand.  Each CTA
-// still computes its own whole block (own x strip, own TMEM), but the shared dy strip is fetched ONCE per cluster:
-// each CTA issues half of its chunks with TMA multicast to both CTAs, which cuts the L2 -> SM operand traffic of a
-// tile from 64 to 48 KiB per stage (the main loop is bound by that feed, profiles/r01_feed_experiment_raw.txt).
-// A stage may only be refilled when BOTH CTAs' UMMAs have retired it (the peer writes into it), so the stage-free
-// commits are multicast to both CTAs' empty barriers, which count two arrivals.
-template <int B, int MH, bool GROUPED, bool PAIR = false>
+template <int B, int MH, bool GROUPED>
 __global__ void __launch_bounds__(kGemmThreads, 1) block_grad_umma_kernel(
     const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
     const GemmParams p) {
@@ -392,7 +372,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) block_grad_umma_kernel(
     prefetch_tmap(map_dy);
     for (int s = 0; s < C::STAGES; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
-      mbar_init(smem_u32(&empty_bar[s]), PAIR ? 2 : 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
     }
     mbar_init(smem_u32(&tmem_full_bar), 1);
     fence_barrier_init();
@@ -400,9 +380,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) block_grad_umma_kernel(
   if (warp == 1) tmem_alloc(smem_u32(&tmem_slot), C::TMEM_COLS);
   tc_fence_before();
   __syncthreads();
-  if (PAIR) cluster_sync_all();        // the peer's barriers exist before anything is multicast to them
   tc_fence_after();
-  const uint32_t pair_rank = PAIR ? cluster_ctarank() : 0u;
   const uint32_t tmem_base = tmem_slot;
   if (threadIdx.x == 0) pdl_launch_dependents();   // the split-K reduce grid may get scheduled (it waits for us)
   if (threadIdx.x == 0) SMT_TRACE(1);                       // barriers + TMEM ready
@@ -418,17 +396,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) block_grad_umma_kernel(
         const uint32_t fb = smem_u32(&full_bar[stage]);
         mbar_expect_tx(fb, C::TX_BYTES);
         const int t0 = (kt_begin + it) * C::KT;
-        if (PAIR) {                      // my half of the shared dy strip, delivered to both CTAs
 #pragma unroll
-          for (int c = 0; c < C::A_LOAD / 2; ++c) {
-            const int cc = (int)pair_rank * (C::A_LOAD / 2) + c;
-            tma_load_2d_multicast(a_addr(stage) + cc * C::CHUNK_BYTES, map_dy, fb, a_col0 + cc * 64, t0, (uint16_t)0x3);
-          }
-        } else {
-#pragma unroll
-          for (int c = 0; c < C::A_ISSUE; ++c)
-            tma_load_2d(a_addr(stage) + c * C::CHUNK_BYTES, map_dy, fb, a_col0 + c * 64, t0);
-        }
+        for (int c = 0; c < C::A_ISSUE; ++c)
+          tma_load_2d(a_addr(stage) + c * C::CHUNK_BYTES, map_dy, fb, a_col0 + c * 64, t0);
 #pragma unroll
         for (int c = 0; c < C::B_LOAD; ++c)
           tma_load_2d(b_addr(stage) + c * C::CHUNK_BYTES, map_x, fb, col * B + c * 64, t0);
@@ -455,8 +425,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) block_grad_umma_kernel(
             umma_f16(tmem_base + mh * B, adesc, bdesc, idesc, (it > 0 || k > 0) ? 1u : 0u);
           }
         }
-        if (PAIR) umma_commit_multicast(smem_u32(&empty_bar[stage]), (uint16_t)0x3);   // tell both producers
-        else umma_commit(smem_u32(&empty_bar[stage]));  // frees the smem stage when these MMAs retire
+        umma_commit(smem_u32(&empty_bar[stage]));  // frees the smem stage when these MMAs retire
       }
       umma_commit(smem_u32(&tmem_full_bar));       // accumulators complete
     }
@@ -504,7 +473,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) block_grad_umma_kernel(
 
   tc_fence_before();
   __syncthreads();
-  if (PAIR) cluster_sync_all();        // nobody leaves while the peer may still signal this CTA's barriers
   if (threadIdx.x == 0) SMT_TRACE(4);                       // epilogue done
   if (warp == 1) {
     tc_fence_after();
@@ -554,7 +522,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) block_grad_umma_kernel(
 // x operand is SPLIT across the pair (CTA r loads x columns [128 r, 128 r + 128) of the block): per 64-token stage a CTA
 // fills  A0 (16 KiB) + B0 half (16 KiB) + A1 (16 KiB) + B1 half (16 KiB) = 64 KiB for the same UMMA work per SM as the
 // single-CTA whole-block tile -- and only 48 KiB (4 instead of 3 stages) when the two items share their dy strip
-// (same operand, same block row: the first `n_paired` items of a grouped launch), because A1 == A0 is then not
+// (same operand, same block row: the host places such pairs on positions (2c, 2c+1)), because A1 == A0 is then not
 // loaded at all.  Fewer TMA boxes and bytes per unit of tensor work is what the single-CTA tile is short of
 // (profiles/r01_kernels.md section 1b).
 // Protocol (the CUTLASS sm100 2-SM scheme): both CTAs run a TMA producer that loads ITS halves with
@@ -972,29 +940,6 @@ int launch_umma(int block, const CUtensorMap& mx, const CUtensorMap& mdy, const 
   return launch_umma_cfg<64, 1, GROUPED>(mx, mdy, gp, pl, st);
 }
 
-// Whole-block tiles of a grouped launch whose items come in row-sharing pairs: clusters of two CTAs.
-int launch_umma_pairs(const GemmParams& gp, int n_paired, cudaStream_t st) {
-  using C = Cfg<256, 2>;
-  auto kern = block_grad_umma_kernel<256, 2, true, true>;
-  SMT_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)n_paired);
-  cfg.blockDim = dim3(kGemmThreads);
-  cfg.dynamicSmemBytes = C::SMEM_BYTES;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  CUtensorMap dummy;
-  memset(&dummy, 0, sizeof(dummy));
-  SMT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, dummy, dummy, gp));
-  return SMT_OK;
-}
-
 // Two whole blocks per CTA pair, cta_group::2 UMMAs (grouped launches of b = 256 blocks that need no split-K).
 int launch_umma_2sm(const GemmParams& gp, int n_items, cudaStream_t st) {
   SMT_CHECK_CUDA(cudaFuncSetAttribute(block_grad_umma_2sm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1189,21 +1134,10 @@ extern "C" SMT_API int smt_encode_operand_map(void* map_host, const void* base, 
 }
 
 namespace {
-// Row-sharing pairs (the first n_paired items) can take the 2-CTA multicast kernel when the launch is big enough to
-// need no split-K (whole-block tiles).  OPT-IN (SMT_GEMM_PAIRS=1): measured on B200 the multicast saves no time (a
-// cluster of 2 does not reduce the L2 -> SM traffic) and the second launch costs ~85 us in bench.py
-// (profiles/r01_kernels.md section 1b).  By default every item goes through the planner.
-bool use_pairs(int n_items, int n_paired, int block, int64_t T) {
-  if (block != 256 || n_paired < 2 || (n_paired & 1) || n_paired > n_items || !env_int("SMT_GEMM_PAIRS", 0)) return false;
-  const Plan pl = make_plan(n_items, block, T);
-  return pl.splits == 1 && pl.mh == 2;
-}
-}  // namespace
-
-namespace {
 // Large grouped launches of b = 256 blocks (no split-K, whole-block tiles) run on SM pairs (cta_group::2): bit-identical
 // to the single-CTA kernel and 3-5 % faster alone / ~1 % in bench.py (profiles/r01_kernels.md section 1b).
-// SMT_GEMM_2SM=0 switches back to the single-CTA kernel.
+// SMT_GEMM_2SM=0 switches back to the single-CTA kernel.  (A cta_group::1 variant that TMA-multicast the shared dy strip
+// inside a 2-CTA cluster was measured no faster than single CTAs and removed; numbers in the same section.)
 bool use_2sm(int n_items, int block, int64_t T) {
   if (block != 256 || n_items < 2 || !env_int("SMT_GEMM_2SM", 1)) return false;
   const Plan pl = make_plan(n_items, block, T);
@@ -1211,21 +1145,16 @@ bool use_2sm(int n_items, int block, int64_t T) {
 }
 }  // namespace
 
-extern "C" SMT_API size_t smt_block_grad_gemm_grouped_workspace_bytes(int n_items, int n_paired, int block, int64_t T) {
+extern "C" SMT_API size_t smt_block_grad_gemm_grouped_workspace_bytes(int n_items, int block, int64_t T) {
   if (n_items <= 0 || T <= 0 || !block_ok(block)) return 0;
-  size_t need = plan_workspace_bytes(make_plan(n_items, block, T));
-  if (use_pairs(n_items, n_paired, block, T) && n_items > n_paired) {
-    const size_t rest = plan_workspace_bytes(make_plan(n_items - n_paired, block, T));
-    if (rest > need) need = rest;
-  }
-  return need;
+  return plan_workspace_bytes(make_plan(n_items, block, T));
 }
 
 extern "C" SMT_API int smt_block_grad_gemm_grouped(const void* maps, const smt_gemm_item* items, int n_items,
-                                                   int n_paired, int64_t T, int block, int in_dtype, void* out_base,
+                                                   int64_t T, int block, int in_dtype, void* out_base,
                                                    int out_dtype, int accumulate, void* workspace,
                                                    size_t workspace_bytes, void* stream) {
-  SMT_CHECK_ARG(n_items >= 0 && T >= 0 && n_paired >= 0, "smt_block_grad_gemm_grouped: negative size");
+  SMT_CHECK_ARG(n_items >= 0 && T >= 0, "smt_block_grad_gemm_grouped: negative size");
   if (n_items == 0 || T == 0) return SMT_OK;
   SMT_CHECK_ARG(block_ok(block), "smt_block_grad_gemm_grouped: block size %d not in {64,128,256}", block);
   SMT_CHECK_ARG(maps && items && out_base, "smt_block_grad_gemm_grouped: null pointer");
@@ -1234,8 +1163,7 @@ extern "C" SMT_API int smt_block_grad_gemm_grouped(const void* maps, const smt_g
   SMT_CHECK_ARG((reinterpret_cast<uintptr_t>(maps) & 63u) == 0 && aligned16(out_base),
                 "smt_block_grad_gemm_grouped: maps must be 64-byte and out_base 16-byte aligned");
   SMT_CHECK_ARG(T < (1ll << 31) - kMaxKTile, "smt_block_grad_gemm_grouped: T too large");
-  SMT_CHECK_ARG(n_paired <= n_items && (n_paired & 1) == 0, "smt_block_grad_gemm_grouped: n_paired must be even and <= n_items");
-  const size_t need_total = smt_block_grad_gemm_grouped_workspace_bytes(n_items, n_paired, block, T);
+  const size_t need_total = smt_block_grad_gemm_grouped_workspace_bytes(n_items, block, T);
   if (need_total > 0 && (workspace == nullptr || workspace_bytes < need_total)) {
     set_error("smt_block_grad_gemm_grouped: workspace too small (%zu < %zu)", workspace_bytes, need_total);
     return SMT_ERR_WORKSPACE;
@@ -1258,33 +1186,21 @@ extern "C" SMT_API int smt_block_grad_gemm_grouped(const void* maps, const smt_g
     set_launch_count(1);
     return SMT_OK;
   }
-  int first_single = 0;
-  if (use_pairs(n_items, n_paired, block, T)) {
-    gp.items = items;
-    gp.splits = 1;
-    gp.kt_per_split = gp.kt_total;
-    if (int rc = launch_umma_pairs(gp, n_paired, st)) return rc;
+  const Plan pl = make_plan(n_items, block, T);
+  const size_t need = plan_workspace_bytes(pl);
+  gp.items = items;
+  gp.ws = need > 0 ? reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + kCounterBytes) : nullptr;
+  gp.counters = use_fused_reduce(pl) ? reinterpret_cast<int*>(workspace) : nullptr;
+  gp.splits = pl.splits;
+  gp.kt_total = pl.kt_total;
+  gp.kt_per_split = pl.kt_per_split;
+  CUtensorMap dummy;
+  memset(&dummy, 0, sizeof(dummy));
+  if (int rc = launch_umma<true>(block, dummy, dummy, gp, pl, st)) return rc;
+  ++launches;
+  if (pl.splits > 1 && gp.counters == nullptr) {
     ++launches;
-    first_single = n_paired;
-  }
-  const int n_rest = n_items - first_single;
-  if (n_rest > 0) {
-    const Plan pl = make_plan(n_rest, block, T);
-    const size_t need = plan_workspace_bytes(pl);
-    gp.items = items + first_single;
-    gp.ws = need > 0 ? reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + kCounterBytes) : nullptr;
-    gp.counters = use_fused_reduce(pl) ? reinterpret_cast<int*>(workspace) : nullptr;
-    gp.splits = pl.splits;
-    gp.kt_total = pl.kt_total;
-    gp.kt_per_split = pl.kt_per_split;
-    CUtensorMap dummy;
-    memset(&dummy, 0, sizeof(dummy));
-    if (int rc = launch_umma<true>(block, dummy, dummy, gp, pl, st)) return rc;
-    ++launches;
-    if (pl.splits > 1 && gp.counters == nullptr) {
-      ++launches;
-      if (int rc = launch_reduce(gp.ws, out_base, gp.items, block, pl, n_rest, out_dtype, accumulate, st)) return rc;
-    }
+    if (int rc = launch_reduce(gp.ws, out_base, gp.items, block, pl, n_items, out_dtype, accumulate, st)) return rc;
   }
   set_launch_count(launches);
   return SMT_OK;

@@ -6,7 +6,6 @@ Every function launches on the CURRENT CUDA stream of the tensors' device.
 from __future__ import annotations
 
 import ctypes as C
-import os
 from typing import Optional, Sequence, Tuple
 
 import torch
@@ -443,14 +442,13 @@ class BlockGradBatch:
         #     once, so every pair must start at an even position;
         #   * a module's unpaired blocks follow its pairs immediately (their strips are still in L2), not at the end of
         #     the launch; an odd one out is carried over to the next module to keep the even alignment.
-        legacy = os.environ.get("SMT_GEMM_PAIRS") == "1" and os.environ.get("SMT_GEMM_2SM") == "0"
-        items, carry, all_pairs, all_singles = [], [], [], []
+        items, carry = [], []
         for x2d, dy2d, idx, out, _b in prs:
             mx, mdy = map_index(x2d), map_index(dy2d)
             off0 = (out.data_ptr() - base_ptr) // esize
             entries = [(mdy, mx, r, c, off0 + i * block * block)
                        for i, (r, c) in sorted(enumerate(idx), key=lambda t: (t[1][0], t[1][1]))]
-            pairs, singles, i, n_carried = [], list(carry), 0, len(carry)
+            pairs, singles, i = [], list(carry), 0
             while i < len(entries):
                 if i + 1 < len(entries) and entries[i][2] == entries[i + 1][2]:
                     pairs += [entries[i], entries[i + 1]]
@@ -458,14 +456,9 @@ class BlockGradBatch:
                 else:
                     singles.append(entries[i])
                     i += 1
-            all_pairs += pairs
-            all_singles += singles[n_carried:]
             carry = [singles.pop()] if len(singles) % 2 else []
             items += pairs + singles
         items += carry
-        n_paired = 0
-        if legacy:      # the opt-in cta_group::1 multicast variant wants all pairs as a prefix of the item list
-            items, n_paired = all_pairs + all_singles, len(all_pairs)
         n_items, n_maps = len(items), len(maps)
         LAST_GROUP.update(items=n_items, operands=n_maps, row_sharing_pairs=sum(
             1 for k in range(0, n_items - 1, 2) if items[k][0] == items[k + 1][0] and items[k][2] == items[k + 1][2]))
@@ -479,10 +472,10 @@ class BlockGradBatch:
                                              in_id, block), "smt_encode_operand_map")
         host[n_maps * 128:].view(item_dt)[:] = np.array(items, dtype=item_dt)
         dev_buf = stage.to(dev, non_blocking=True)
-        ws_bytes = lib.smt_block_grad_gemm_grouped_workspace_bytes(n_items, n_paired, block, T)
+        ws_bytes = lib.smt_block_grad_gemm_grouped_workspace_bytes(n_items, block, T)
         ws = _workspace(ws_bytes, dev)
         with _timed("block_grad_gemm", dev, (n_items, block, T)):
-            check(lib.smt_block_grad_gemm_grouped(dev_buf.data_ptr(), dev_buf.data_ptr() + n_maps * 128, n_items, n_paired,
+            check(lib.smt_block_grad_gemm_grouped(dev_buf.data_ptr(), dev_buf.data_ptr() + n_maps * 128, n_items,
                                                   T, block, in_id, base_ptr, dtype_id(out_dt), 1 if accumulate else 0,
                                                   ptr(ws), ws_bytes, stream_ptr(dev)), "smt_block_grad_gemm_grouped")
         _count(lib.smt_last_launch_count())

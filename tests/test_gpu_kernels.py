@@ -385,47 +385,6 @@ def test_grouped_gemm_large_group_no_split(ops):
         assert (got - want).abs().max().item() <= 2e-5 * want.abs().max().item()
 
 
-def test_grouped_gemm_row_sharing_pairs_multicast(ops, monkeypatch):
-    """Blocks of one block row share their dy strip: in a launch big enough to need no split-K they run as 2-CTA
-    clusters that fetch the strip once and TMA-multicast it (opt-in variant, SMT_GEMM_PAIRS=1).  Same per-tile arithmetic as the single-CTA kernel, so the
-    results must be BIT-identical with pairing switched off, and match the dense reference."""
-    torch.manual_seed(3)
-    T, b = 640, 256
-    P = 4
-    xs = [torch.randn(T, 1536, device="cuda").bfloat16() for _ in range(P)]
-    dys = [torch.randn(T, 2048, device="cuda").bfloat16() for _ in range(P)]
-    # rows with 1, 2, 3, 5 and 6 selected columns: pairs plus left-over singles, 4 problems x 43 blocks = 172 tiles
-    idx = [(0, 4)] + [(1, c) for c in (0, 5)] + [(2, c) for c in (1, 2, 3)] + [(3, c) for c in (0, 1, 2, 4, 5)] + \
-          [(r, c) for r in (4, 5, 6, 7, 0, 2, 5, 6) for c in range(6)]
-    idx = list(dict.fromkeys(idx))
-    n = len(idx)
-    assert P * n >= 148
-
-    def run():
-        out = torch.zeros(P * n * b * b, device="cuda")
-        batch = ops.BlockGradBatch()
-        for i in range(P):
-            batch.add(xs[i], dys[i], idx, out[i * n * b * b:(i + 1) * n * b * b].view(-1, b), b)
-        assert batch.flush(accumulate=False) == 1
-        return out
-
-    monkeypatch.setenv("SMT_GEMM_2SM", "0")                        # compare the two cta_group::1 variants
-    monkeypatch.setenv("SMT_GEMM_PAIRS", "1")                      # opt-in multicast clusters
-    launches0 = ops.LAUNCHES["total"]
-    paired = run()
-    assert ops.LAUNCHES["total"] - launches0 == 2                  # pair clusters + the left-over singles
-    monkeypatch.delenv("SMT_GEMM_PAIRS", raising=False)
-    launches0 = ops.LAUNCHES["total"]
-    single = run()
-    assert ops.LAUNCHES["total"] - launches0 == 1
-    assert torch.equal(paired, single)
-    for i in range(P):
-        ref = dys[i].float().t() @ xs[i].float()
-        got = paired[i * n * b * b:(i + 1) * n * b * b].view(n, b, b)
-        want = torch.stack([ref[r * b:(r + 1) * b, c * b:(c + 1) * b] for r, c in idx])
-        assert (got - want).abs().max().item() <= 2e-5 * want.abs().max().item()
-
-
 @pytest.mark.parametrize("out_dtype,accumulate", [(torch.float32, False), (torch.bfloat16, True)])
 def test_grouped_gemm_2sm_cta_pairs(ops, monkeypatch, out_dtype, accumulate):
     """cta_group::2 kernel (the default for large grouped b = 256 launches; SMT_GEMM_2SM=0 = single-CTA kernel): two

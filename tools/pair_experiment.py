@@ -1,4 +1,5 @@
-"""Grouped launch of row-sharing block pairs: 2-CTA multicast clusters vs the same items as single CTAs."""
+"""Grouped launch of row-sharing block pairs: the cta_group::2 kernel (two blocks per SM pair) vs single-CTA tiles.
+(An earlier revision also timed a cta_group::1 cluster variant with TMA multicast: profiles/r01_pair_experiment_raw.txt.)"""
 import os
 import sys
 
@@ -55,16 +56,12 @@ for label, n_mod, rows, cols, per_row in (("k/v-like modules: 4x16 blocks, 8 per
         batch.flush(accumulate=False)
 
     fl = 2.0 * b * b * T * n
-    os.environ["SMT_GEMM_2SM"] = "0"
-    os.environ["SMT_GEMM_PAIRS"] = "1"
-    t_pair = timeit(run)
-    os.environ.pop("SMT_GEMM_PAIRS", None)
     os.environ["SMT_GEMM_2SM"] = "1"
     t_2sm = timeit(run)
     os.environ["SMT_GEMM_2SM"] = "0"
     t_single = timeit(run)
     os.environ.pop("SMT_GEMM_2SM", None)
-    print(f"{label}: {n} blocks: pairs {t_pair:.1f} us ({fl / t_pair / 1e6:.0f} TF/s)  singles {t_single:.1f} us ({fl / t_single / 1e6:.0f} TF/s)  "
+    print(f"{label}: {n} blocks: singles {t_single:.1f} us ({fl / t_single / 1e6:.0f} TF/s)  "
           f"cta_group::2 {t_2sm:.1f} us ({fl / t_2sm / 1e6:.0f} TF/s)",
           flush=True)
     del xs, dys
