@@ -666,3 +666,36 @@ def test_channel_freeze_and_convert_on_tiny_llama(api):
         opt.step(); opt.zero_grad()
         losses.append(out.loss.item())
     assert losses[-1] < losses[0]
+
+
+def test_channel_modules_in_merged_export_and_resume(api):
+    """checkpoint.py treats channel-sparse modules like block-sparse ones: the merged state dict has the trained columns
+    written back and no `selected_weight` keys; smt_state / load_smt_state round-trip the compact parameter."""
+    M, _H = api
+    from sparse_matrix_tuning_b200 import checkpoint as CK
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.layers = torch.nn.ModuleList([torch.nn.Linear(192, 320, bias=False), torch.nn.Linear(320, 64, bias=False)])
+
+    torch.manual_seed(3)
+    net = Net().cuda().bfloat16()
+    idx = [5, 191, 64]
+    net.layers[0] = M.LinearLayer_ChannelSparsity(net.layers[0].weight, bias=None, index_list=idx)
+    layer = net.layers[0]
+    w0 = layer.weight.detach().clone()
+    with torch.no_grad():
+        layer.selected_weight.add_(1.0)
+    merged = CK.merged_state_dict(net)
+    assert set(merged) == {"layers.0.weight", "layers.1.weight"}
+    assert torch.equal(merged["layers.0.weight"][:, idx].t().contiguous(), layer.selected_weight.detach())
+    keep = [c for c in range(192) if c not in idx]
+    assert torch.equal(merged["layers.0.weight"][:, keep], w0[:, keep])
+    state = CK.smt_state(net)
+    assert state["index_lists"]["layers.0"] == idx and state["block"]["layers.0"] is None
+    with torch.no_grad():
+        layer.selected_weight.zero_()
+    CK.load_smt_state(net, state)
+    assert torch.equal(layer.selected_weight.detach(), state["selected_weight"]["layers.0"])
+    assert torch.equal(layer.weight[:, idx].t().contiguous(), layer.selected_weight.detach())
