@@ -429,3 +429,31 @@ def test_grouped_gemm_2sm_cta_pairs(ops, monkeypatch, out_dtype, accumulate):
             want = want + init[offs[i]:offs[i + 1]].view(len(uses[i]), b, b).float()
         tol = 2e-5 if out_dtype == torch.float32 else 2 ** -7
         assert (got - want).abs().max().item() <= tol * want.abs().max().item()
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("block", [64, 128, 256])
+def test_block_grad_gemm_token_count_edges(ops, block, dtype):
+    """Ragged token counts around every stage height in use (64 / 128 / 256 tokens) and around split-K boundaries:
+    the last TMA box is zero-filled past T, so any T must give the dense result.  Single-problem and grouped entry
+    points, fp32 output, tolerance = fp32 accumulation error."""
+    torch.manual_seed(block)
+    fin, fout = 512, 768
+    g = torch.Generator().manual_seed(block)
+    nb = (fout // block) * (fin // block)
+    perm = torch.randperm(nb, generator=g)[:min(nb, 7)].tolist()
+    idx = [(p // (fin // block), p % (fin // block)) for p in perm]
+    rc = ops.make_block_rc(idx, "cuda")
+    for T in (1, 15, 16, 17, 63, 64, 65, 127, 128, 129, 255, 256, 257, 511, 513, 1023, 1025, 2047, 2049, 4095, 4097):
+        x = torch.randn(T, fin, device="cuda").to(dtype)
+        dy = torch.randn(T, fout, device="cuda").to(dtype)
+        ref = dy.float().t() @ x.float()
+        want = torch.cat([ref[r * block:(r + 1) * block, c * block:(c + 1) * block] for r, c in idx])
+        scale = max(want.abs().max().item(), 1e-3)
+        got = ops.block_grad_gemm(x, dy, rc, block, out_dtype=torch.float32)
+        assert (got - want).abs().max().item() <= 2e-5 * scale, (T, "single")
+        out = torch.zeros(len(idx) * block, block, device="cuda")
+        batch = ops.BlockGradBatch()
+        batch.add(x, dy, idx, out, block)
+        batch.flush(accumulate=False)
+        assert (out - want).abs().max().item() <= 2e-5 * scale, (T, "grouped")
