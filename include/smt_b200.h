@@ -172,6 +172,9 @@ typedef struct smt_gemm_item {
 SMT_API int smt_encode_operand_map(void* map_host, const void* base, int64_t features, int64_t T, int64_t ld,
                                    int dtype, int block);
 SMT_API size_t smt_block_grad_gemm_grouped_workspace_bytes(int n_items, int block, int64_t T);
+/* 1 when a grouped launch of this shape runs the cta_group::2 kernel, 0 when it runs single-CTA tiles (introspection
+ * for tests and reports; depends on the planner and on SMT_GEMM_2SM). */
+SMT_API int smt_block_grad_gemm_grouped_uses_2sm(int n_items, int block, int64_t T);
 SMT_API int smt_block_grad_gemm_grouped(const void* maps, const smt_gemm_item* items, int n_items,
                                         int64_t T, int block, int in_dtype, void* out_base, int out_dtype,
                                         int accumulate, void* workspace, size_t workspace_bytes, void* stream);

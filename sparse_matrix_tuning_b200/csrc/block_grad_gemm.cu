@@ -1145,6 +1145,10 @@ bool use_2sm(int n_items, int block, int64_t T) {
 }
 }  // namespace
 
+extern "C" SMT_API int smt_block_grad_gemm_grouped_uses_2sm(int n_items, int block, int64_t T) {
+  return (n_items > 0 && T > 0 && block_ok(block) && use_2sm(n_items, block, T)) ? 1 : 0;
+}
+
 extern "C" SMT_API size_t smt_block_grad_gemm_grouped_workspace_bytes(int n_items, int block, int64_t T) {
   if (n_items <= 0 || T <= 0 || !block_ok(block)) return 0;
   return plan_workspace_bytes(make_plan(n_items, block, T));

@@ -460,7 +460,9 @@ class BlockGradBatch:
             items += pairs + singles
         items += carry
         n_items, n_maps = len(items), len(maps)
-        LAST_GROUP.update(items=n_items, operands=n_maps, row_sharing_pairs=sum(
+        LAST_GROUP.update(items=n_items, operands=n_maps,
+                          cta_group_2=bool(lib.smt_block_grad_gemm_grouped_uses_2sm(n_items, block, T)),
+                          row_sharing_pairs=sum(
             1 for k in range(0, n_items - 1, 2) if items[k][0] == items[k + 1][0] and items[k][2] == items[k + 1][2]))
         item_dt = np.dtype([("map_dy", "<u4"), ("map_x", "<u4"), ("row", "<i4"), ("col", "<i4"), ("out_off", "<i8")])
         nbytes = n_maps * 128 + n_items * item_dt.itemsize

@@ -419,7 +419,7 @@ def test_grouped_gemm_2sm_cta_pairs(ops, monkeypatch, out_dtype, accumulate):
     single, _ = run()
     monkeypatch.delenv("SMT_GEMM_2SM", raising=False)              # default: cta_group::2
     paired, launches = run()
-    assert launches == 1
+    assert launches == 1 and ops.LAST_GROUP["cta_group_2"] and ops.LAST_GROUP["row_sharing_pairs"] > 40
     assert torch.equal(paired, single)
     for i in range(P):
         ref = dys[i].float().t() @ xs[i].float()
@@ -457,3 +457,24 @@ def test_block_grad_gemm_token_count_edges(ops, block, dtype):
         batch.add(x, dy, idx, out, block)
         batch.flush(accumulate=False)
         assert (out - want).abs().max().item() <= 2e-5 * scale, (T, "grouped")
+
+
+def test_grouped_gemm_2sm_token_count_edges(ops):
+    """The cta_group::2 kernel with ragged / tiny token counts (zero-filled last stage, a single stage, one token)."""
+    torch.manual_seed(4)
+    b, P = 256, 4
+    idx = [(r, c) for r in range(5) for c in range(8)]                  # 40 blocks per problem, 160 items
+    for T in (1, 63, 64, 65, 200, 257):
+        xs = [torch.randn(T, 2048, device="cuda").bfloat16() for _ in range(P)]
+        dys = [torch.randn(T, 1280, device="cuda").bfloat16() for _ in range(P)]
+        out = torch.zeros(P * len(idx) * b * b, device="cuda")
+        batch = ops.BlockGradBatch()
+        for i in range(P):
+            batch.add(xs[i], dys[i], idx, out[i * len(idx) * b * b:(i + 1) * len(idx) * b * b].view(-1, b), b)
+        batch.flush(accumulate=False)
+        assert ops.LAST_GROUP["cta_group_2"], T
+        for i in range(P):
+            ref = dys[i].float().t() @ xs[i].float()
+            got = out[i * len(idx) * b * b:(i + 1) * len(idx) * b * b].view(len(idx), b, b)
+            want = torch.stack([ref[r * b:(r + 1) * b, c * b:(c + 1) * b] for r, c in idx])
+            assert (got - want).abs().max().item() <= 2e-5 * max(want.abs().max().item(), 1e-3), T
