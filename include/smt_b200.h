@@ -167,7 +167,14 @@ typedef struct smt_gemm_item {
   int32_t  row;      /* block row    (out_features / b index)            */
   int32_t  col;      /* block column (in_features  / b index)            */
   int64_t  out_off;  /* element offset of this block's [b, b] output     */
+  uint32_t flags;    /* SMT_ITEM_* bits                                   */
+  int32_t  sq_slot;  /* >= 0: sq_partials[sq_slot], [sq_slot + 1] receive the sum of squares of the values STORED for
+                        this block (after accumulation and rounding to out_dtype; upper / lower half of the rows for
+                        b = 256, [total, 0] for smaller blocks); < 0: none                                            */
 } smt_gemm_item;
+/* item flag: overwrite this block's output even when the launch-level `accumulate` is set (first micro-batch after a
+ * lazy zero_grad: no memset of the gradient buffer, no read-modify-write in the epilogue) */
+enum { SMT_ITEM_OVERWRITE = 1 };
 /* `block` = the block size of the launch the descriptor will be used in (it fixes the TMA box height). */
 SMT_API int smt_encode_operand_map(void* map_host, const void* base, int64_t features, int64_t T, int64_t ld,
                                    int dtype, int block);
@@ -175,9 +182,14 @@ SMT_API size_t smt_block_grad_gemm_grouped_workspace_bytes(int n_items, int bloc
 /* 1 when a grouped launch of this shape runs the cta_group::2 kernel, 0 when it runs single-CTA tiles (introspection
  * for tests and reports; depends on the planner and on SMT_GEMM_2SM). */
 SMT_API int smt_block_grad_gemm_grouped_uses_2sm(int n_items, int block, int64_t T);
+/* `sq_partials` (device, fp32, may be NULL): per-block sums of squares, see smt_gemm_item.sq_slot.  They are produced by
+ * the launches that need no split-K (smt_block_grad_gemm_grouped_emits_sq tells); the sums are deterministic (fixed
+ * order inside each CTA) and feed the clip of smt_compact_adam without a separate pass over the gradient buffer. */
+SMT_API int smt_block_grad_gemm_grouped_emits_sq(int n_items, int block, int64_t T);
 SMT_API int smt_block_grad_gemm_grouped(const void* maps, const smt_gemm_item* items, int n_items,
                                         int64_t T, int block, int in_dtype, void* out_base, int out_dtype,
-                                        int accumulate, void* workspace, size_t workspace_bytes, void* stream);
+                                        int accumulate, float* sq_partials, void* workspace, size_t workspace_bytes,
+                                        void* stream);
 /* debug: register a device buffer of 8*max_ctas uint64; each CTA of smt_block_grad_gemm stamps %globaltimer at its
  * phase boundaries (tools/trace_gemm.py). NULL switches tracing off. Not for production use. */
 SMT_API int smt_debug_set_gemm_trace(void* dev_buf, int max_ctas);
@@ -195,8 +207,10 @@ SMT_API int smt_grad_sqnorm(const void* grad, int grad_dtype, int64_t n, float* 
 /* AdamW step (DeepSpeed FusedAdam adam_w_mode, fine_tune.py:352-363) over the flat compact state,
  * fused with global-norm clipping (deepspeed_helpers.py:87) and with the write-back of the updated
  * blocks into the dense weights (smt.py:332-341), so no scatter is needed in forward.
- *   g      = grad * grad_scale * clip,   clip = min(1, max_norm / (grad_scale*sqrt(*sqnorm) + 1e-6))
- *            (clip = 1 when sqnorm == NULL or max_norm <= 0)
+ *   g      = grad * grad_scale * clip,   clip = min(1, max_norm / (grad_scale*sqrt(S) + 1e-6)),
+ *            S = sqnorm[0] + ... + sqnorm[n_sqnorm-1] summed in a fixed order inside the kernel (n_sqnorm = 1: the
+ *            scalar of smt_grad_sqnorm; > 1: the per-block partials of the GEMM epilogue or per-chunk partials of a
+ *            data-parallel exchange);  clip = 1 when sqnorm == NULL or max_norm <= 0
  *   m      = b1*m + (1-b1)*g ;  v = b2*v + (1-b2)*g*g
  *   update = (m/bc1) / (sqrt(v/bc2) + eps) + wd*p ;  p -= lr*update        (p = fp32 master)
  * then compact_out[i] (optional) and W blocks (optional, via `table`) receive p rounded to their
@@ -205,7 +219,7 @@ SMT_API int smt_compact_adam(float* master, float* exp_avg, float* exp_avg_sq,
                      const void* grad, int grad_dtype, int64_t n_elems,
                      float lr, float beta1, float beta2, float eps, float weight_decay,
                      float bias_correction1, float bias_correction2,
-                     float grad_scale, const float* sqnorm, float max_norm,
+                     float grad_scale, const float* sqnorm, int n_sqnorm, float max_norm,
                      void* compact_out, int compact_dtype,
                      const smt_block_ref* table, int n_blocks, int block, int w_dtype,
                      void* stream);

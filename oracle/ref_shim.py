@@ -18,7 +18,20 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("SMT_REFERENCE_ROOT", "/root/reference")
+# `oracle/_ref/` = the two reference modules staged, unmodified, by `oracle/build_ref.py` (git-ignored, but it travels to
+# the GPU box with the snapshot): lets `bench.py` time the reference ITSELF where `/root/reference` does not exist.
+STAGED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def _pick_root() -> str:
+    env = os.environ.get("SMT_REFERENCE_ROOT")
+    for cand in (env, STAGED_ROOT, "/root/reference"):
+        if cand and os.path.isfile(os.path.join(cand, "deepspeed", "smt", "smt.py")):
+            return cand
+    return env or "/root/reference"
+
+
+REFERENCE_ROOT = _pick_root()
 
 
 def reference_available() -> bool:

@@ -288,6 +288,34 @@ def clip_coef(sqnorm: np.float32, grad_scale: np.float32, max_norm: np.float32) 
     return f(grad_scale) * coef if coef < 1 else f(grad_scale)
 
 
+def partial_sqnorm_total(partials, threads: int = 256) -> np.float32:
+    """Total of several partial sums of squares in the FIXED order the Adam kernel uses when it is handed the
+    per-block slots of the GEMM epilogue / per-chunk norms of a data-parallel exchange (no reference counterpart: the
+    reference's clip, helpers/deepspeed_helpers.py:87, takes one norm over all gradients; the order only fixes the last
+    fp32 bits): thread t adds partials[t], partials[t + threads], ... sequentially, each warp of 32 threads is reduced
+    by an xor butterfly (16, 8, 4, 2, 1), and the per-warp results by the same butterfly."""
+    f = np.float32
+    partials = np.asarray(partials, dtype=np.float32).reshape(-1)
+    per_thread = np.zeros(threads, dtype=np.float32)
+    for t in range(min(threads, len(partials))):
+        acc = f(0)
+        for val in partials[t::threads]:
+            acc = f(acc + val)
+        per_thread[t] = acc
+
+    def butterfly(vals):
+        vals = vals.astype(np.float32).copy()
+        lanes = np.arange(32)
+        for o in (16, 8, 4, 2, 1):
+            vals = (vals + vals[lanes ^ o]).astype(np.float32)
+        return vals[0]
+
+    warps = np.zeros(32, dtype=np.float32)
+    for w in range(threads // 32):
+        warps[w] = butterfly(per_thread[32 * w:32 * w + 32])
+    return f(butterfly(warps))
+
+
 def adamw_fused_step(p, m, v, g, *, lr, beta1, beta2, eps, weight_decay, step, gscale=1.0):
     """One multi_tensor_adam (adam_w_mode=1, bias_correction=1) update in fp32, every operation rounded
     individually (no FMA contraction):

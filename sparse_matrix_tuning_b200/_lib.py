@@ -29,7 +29,10 @@ class BlockRef(C.Structure):
 class GemmItem(C.Structure):
     """Mirror of `smt_gemm_item`."""
     _fields_ = [("map_dy", C.c_uint32), ("map_x", C.c_uint32), ("row", C.c_int32), ("col", C.c_int32),
-                ("out_off", C.c_int64)]
+                ("out_off", C.c_int64), ("flags", C.c_uint32), ("sq_slot", C.c_int32)]
+
+
+ITEM_OVERWRITE = 1   # SMT_ITEM_OVERWRITE
 
 
 class SMTLibraryError(RuntimeError):
@@ -62,15 +65,16 @@ _SIGNATURES = {
     "smt_encode_operand_map": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int]),
     "smt_block_grad_gemm_grouped_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int64]),
     "smt_block_grad_gemm_grouped_uses_2sm": (C.c_int, [C.c_int, C.c_int, C.c_int64]),
+    "smt_block_grad_gemm_grouped_emits_sq": (C.c_int, [C.c_int, C.c_int, C.c_int64]),
     "smt_block_grad_gemm_grouped": (C.c_int, [_P, _P, C.c_int, C.c_int64, C.c_int, C.c_int, _P, C.c_int,
-                                              C.c_int, _P, C.c_size_t, _P]),
+                                              C.c_int, _P, _P, C.c_size_t, _P]),
     "smt_block_grad_gemm_plan": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_int),
                                            C.POINTER(C.c_int)]),
     "smt_grad_sqnorm_workspace_bytes": (C.c_size_t, []),
     "smt_grad_sqnorm": (C.c_int, [_P, C.c_int, C.c_int64, _P, _P, C.c_size_t, _P]),
     "smt_compact_adam": (C.c_int, [_P, _P, _P, _P, C.c_int, C.c_int64,
                                    C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
-                                   C.c_float, _P, C.c_float, _P, C.c_int, _P, C.c_int, C.c_int, C.c_int, _P]),
+                                   C.c_float, _P, C.c_int, C.c_float, _P, C.c_int, _P, C.c_int, C.c_int, C.c_int, _P]),
 }
 EXPORTS = tuple(_SIGNATURES)
 

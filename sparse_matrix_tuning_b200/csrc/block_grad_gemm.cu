@@ -230,6 +230,7 @@ struct GemmParams {
   const CUtensorMap* maps;        // grouped: tensor maps in global memory (indexed by the items)
   void* out;                      // G base (single problem: block i at i*b*b; grouped: items[i].out_off)
   float* ws;                      // fp32 partial tiles when splits > 1
+  float* sq;                      // grouped, no split-K: per-block sum-of-squares slots (items[i].sq_slot), or NULL
   int* counters;                  // fused reduction: 2 self-resetting ints per tile (NULL = separate reduce kernel)
   unsigned long long* trace;      // debug (SMT_GEMM_TRACE=1): 8 globaltimer stamps per CTA, else NULL
   int splits;
@@ -240,8 +241,10 @@ struct GemmParams {
   int in_fmt;                     // 0 = f16, 1 = bf16
 };
 
+// Stores 4 values (optionally added to what is there) and returns the sum of squares of the values as STORED, i.e.
+// after the rounding to the output type (the clip norm is defined on the gradient buffer's contents).
 template <int ODT, bool ACC>
-__device__ __forceinline__ void store4(void* out_base, int64_t off, float4 v) {
+__device__ __forceinline__ float store4(void* out_base, int64_t off, float4 v) {
   if (ODT == SMT_F32) {
     float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(out_base) + off);
     if (ACC) {
@@ -249,6 +252,7 @@ __device__ __forceinline__ void store4(void* out_base, int64_t off, float4 v) {
       v.x += old.x; v.y += old.y; v.z += old.z; v.w += old.w;
     }
     *o = v;
+    return (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
   } else {
     uint2* o = reinterpret_cast<uint2*>(reinterpret_cast<uint16_t*>(out_base) + off);
     if (ACC) {
@@ -263,17 +267,27 @@ __device__ __forceinline__ void store4(void* out_base, int64_t off, float4 v) {
       }
     }
     uint2 u;
-    if (ODT == SMT_BF16) { u.x = pack_bf16x2(v.x, v.y); u.y = pack_bf16x2(v.z, v.w); }
-    else { u.x = pack_f16x2(v.x, v.y); u.y = pack_f16x2(v.z, v.w); }
+    float4 w;
+    if (ODT == SMT_BF16) {
+      u.x = pack_bf16x2(v.x, v.y); u.y = pack_bf16x2(v.z, v.w);
+      w = make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u),
+                      __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
+    } else {
+      u.x = pack_f16x2(v.x, v.y); u.y = pack_f16x2(v.z, v.w);
+      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+      const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+      w = make_float4(a.x, a.y, b.x, b.y);
+    }
     *o = u;
+    return (w.x * w.x + w.y * w.y) + (w.z * w.z + w.w * w.w);
   }
 }
 
 // One 32x32 fp32 accumulator sub-tile (lane = row, r[] = 32 columns) -> global, transposed through a per-warp
 // shared-memory buffer so that each store instruction covers 4 rows x 128 B (fp32) / 64 B (16-bit).
 template <int ODT, bool ACC>
-__device__ __forceinline__ void store_subtile(float* stage, const uint32_t (&r)[32], int lane, void* out_base,
-                                              int64_t off00, int ld) {
+__device__ __forceinline__ float store_subtile(float* stage, const uint32_t (&r)[32], int lane, void* out_base,
+                                               int64_t off00, int ld) {
   float4* mine = reinterpret_cast<float4*>(stage + lane * kStageRow);
 #pragma unroll
   for (int q = 0; q < 8; ++q)
@@ -281,13 +295,28 @@ __device__ __forceinline__ void store_subtile(float* stage, const uint32_t (&r)[
                           __uint_as_float(r[4 * q + 3]));
   __syncwarp();
   const int sub = lane >> 3, cv = (lane & 7) * 4;
+  float sq = 0.f;
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     const int row = it * 4 + sub;
     const float4 v = *reinterpret_cast<const float4*>(stage + row * kStageRow + cv);
-    store4<ODT, ACC>(out_base, off00 + (int64_t)row * ld + cv, v);
+    sq += store4<ODT, ACC>(out_base, off00 + (int64_t)row * ld + cv, v);
   }
   __syncwarp();
+  return sq;
+}
+
+// Dispatch on (output type, accumulate) for one sub-tile; returns the thread's sum of squares of the stored values.
+__device__ __forceinline__ float store_subtile_any(int out_dtype, bool acc, float* stage, const uint32_t (&r)[32],
+                                                   int lane, void* out_base, int64_t off, int ld) {
+  if (out_dtype == SMT_F32)
+    return acc ? store_subtile<SMT_F32, true>(stage, r, lane, out_base, off, ld)
+               : store_subtile<SMT_F32, false>(stage, r, lane, out_base, off, ld);
+  if (out_dtype == SMT_BF16)
+    return acc ? store_subtile<SMT_BF16, true>(stage, r, lane, out_base, off, ld)
+               : store_subtile<SMT_BF16, false>(stage, r, lane, out_base, off, ld);
+  return acc ? store_subtile<SMT_F16, true>(stage, r, lane, out_base, off, ld)
+             : store_subtile<SMT_F16, false>(stage, r, lane, out_base, off, ld);
 }
 
 __device__ __forceinline__ float4 ld_cg_f4(const float* p) {   // L2-coherent load (data written by other CTAs of this grid)
@@ -337,6 +366,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) block_grad_umma_kernel(
   __shared__ __align__(8) uint64_t empty_bar[C::STAGES];
   __shared__ __align__(8) uint64_t tmem_full_bar;
   __shared__ uint32_t tmem_slot;
+  __shared__ float sq_warp[kEpiWarps][2];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x, split = blockIdx.y;
@@ -356,12 +386,16 @@ __global__ void __launch_bounds__(kGemmThreads, 1) block_grad_umma_kernel(
   const CUtensorMap* map_x = &tmap_x;
   const CUtensorMap* map_dy = &tmap_dy;
   int64_t out_off;                       // element offset of this tile's first output row
+  bool acc_out = p.accumulate != 0;      // add into the output (an item may ask for a plain overwrite instead)
+  int sq_slot = -1;
   if (GROUPED) {
     const smt_gemm_item item = p.items[blk];
     row = item.row; col = item.col;
     map_x = p.maps + item.map_x;
     map_dy = p.maps + item.map_dy;
     out_off = item.out_off + (int64_t)half * 128 * B;
+    if (item.flags & SMT_ITEM_OVERWRITE) acc_out = false;
+    if (p.sq != nullptr && p.splits == 1) sq_slot = item.sq_slot;
   } else {
     row = p.block_rc[2 * blk]; col = p.block_rc[2 * blk + 1];
     out_off = (int64_t)tile * C::TILE_ELEMS;
@@ -438,6 +472,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) block_grad_umma_kernel(
     mbar_wait(smem_u32(&tmem_full_bar), 0);
     tc_fence_after();
     if (ew == 0) SMT_TRACE(3);                              // accumulators complete
+    float sq0 = 0.f, sq1 = 0.f;
     if (q * 32 < ROWS_PER_MH) {
       // all MMAs have retired => the pipeline buffers are dead; reuse them as transpose staging
       float* stage = reinterpret_cast<float*>(smem_gen) + ew * 32 * kStageRow;
@@ -454,20 +489,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1) block_grad_umma_kernel(
           if (!final_out) {
             store_subtile<SMT_F32, false>(stage, r, lane, part, off_in_tile, B);
           } else {
-            const int64_t off = out_off + off_in_tile;
-            if (p.out_dtype == SMT_F32) {
-              if (p.accumulate) store_subtile<SMT_F32, true>(stage, r, lane, p.out, off, B);
-              else store_subtile<SMT_F32, false>(stage, r, lane, p.out, off, B);
-            } else if (p.out_dtype == SMT_BF16) {
-              if (p.accumulate) store_subtile<SMT_BF16, true>(stage, r, lane, p.out, off, B);
-              else store_subtile<SMT_BF16, false>(stage, r, lane, p.out, off, B);
-            } else {
-              if (p.accumulate) store_subtile<SMT_F16, true>(stage, r, lane, p.out, off, B);
-              else store_subtile<SMT_F16, false>(stage, r, lane, p.out, off, B);
-            }
+            const float sv = store_subtile_any(p.out_dtype, acc_out, stage, r, lane, p.out, out_off + off_in_tile, B);
+            if (mh == 0) sq0 += sv; else sq1 += sv;
           }
         }
       }
+    }
+    if (sq_slot >= 0) {
+      const float s0 = warp_sum(sq0), s1 = warp_sum(sq1);
+      if (lane == 0) { sq_warp[ew][0] = s0; sq_warp[ew][1] = s1; }
     }
   }
 
@@ -477,6 +507,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) block_grad_umma_kernel(
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+  if (sq_slot >= 0 && threadIdx.x == 0) {
+    // fixed-order sum over the epilogue warps: deterministic.  Slot layout: [rows 0-127, rows 128-255] of a b = 256
+    // block, [total, 0] for smaller blocks.
+    float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+    for (int w = 0; w < kEpiWarps; ++w) { t0 += sq_warp[w][0]; t1 += sq_warp[w][1]; }
+    if (C::TILES_PER_BLOCK == 2) {
+      p.sq[sq_slot + half] = t0;
+    } else {
+      p.sq[sq_slot] = t0;
+      p.sq[sq_slot + 1] = t1;
+    }
   }
 
   if (p.counters != nullptr) {
@@ -501,9 +544,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) block_grad_umma_kernel(
     const int e_begin = split * chunk;
     const int e_end = min(e_begin + chunk, C::TILE_ELEMS);
     const float* part0 = p.ws + (int64_t)tile * p.splits * C::TILE_ELEMS;
-    if (p.out_dtype == SMT_F32) fused_reduce_slice<SMT_F32>(part0, p.splits, C::TILE_ELEMS, e_begin, e_end, p.out, out_off, p.accumulate != 0);
-    else if (p.out_dtype == SMT_BF16) fused_reduce_slice<SMT_BF16>(part0, p.splits, C::TILE_ELEMS, e_begin, e_end, p.out, out_off, p.accumulate != 0);
-    else fused_reduce_slice<SMT_F16>(part0, p.splits, C::TILE_ELEMS, e_begin, e_end, p.out, out_off, p.accumulate != 0);
+    if (p.out_dtype == SMT_F32) fused_reduce_slice<SMT_F32>(part0, p.splits, C::TILE_ELEMS, e_begin, e_end, p.out, out_off, acc_out);
+    else if (p.out_dtype == SMT_BF16) fused_reduce_slice<SMT_BF16>(part0, p.splits, C::TILE_ELEMS, e_begin, e_end, p.out, out_off, acc_out);
+    else fused_reduce_slice<SMT_F16>(part0, p.splits, C::TILE_ELEMS, e_begin, e_end, p.out, out_off, acc_out);
     __syncthreads();
     if (threadIdx.x == 0) {
       SMT_TRACE(6);                                         // slice reduced
@@ -571,6 +614,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) block_grad_umma_2sm_kernel(co
   __shared__ __align__(8) uint64_t empty_bar[k2smMaxStages];
   __shared__ __align__(8) uint64_t tmem_full_bar;
   __shared__ uint32_t tmem_slot;
+  __shared__ float sq_warp[kEpiWarps][2];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();               // 0 = leader (issues the UMMAs)
@@ -667,26 +711,24 @@ __global__ void __launch_bounds__(kGemmThreads, 1) block_grad_umma_2sm_kernel(co
     mbar_wait(smem_u32(&tmem_full_bar), 0);
     tc_fence_after();
     float* stage = reinterpret_cast<float*>(smem_gen) + ew * 32 * kStageRow;   // pipeline buffers are dead by now
+    float sq0 = 0.f, sq1 = 0.f;
 #pragma unroll 1
     for (int blk = 0; blk < (has2 ? 2 : 1); ++blk) {
-      const int64_t out0 = (blk == 0 ? it0.out_off : it1.out_off) + (int64_t)((int)rank * 128 + q * 32) * B;
+      const smt_gemm_item& item = blk == 0 ? it0 : it1;
+      const int64_t out0 = item.out_off + (int64_t)((int)rank * 128 + q * 32) * B;
+      const bool acc_out = p.accumulate != 0 && !(item.flags & SMT_ITEM_OVERWRITE);
 #pragma unroll 1
       for (int cc = par; cc < B / 32; cc += kEpiWarps / 4) {
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(blk * B + cc * 32), r);
         tmem_ld_wait();
-        const int64_t off = out0 + cc * 32;
-        if (p.out_dtype == SMT_F32) {
-          if (p.accumulate) store_subtile<SMT_F32, true>(stage, r, lane, p.out, off, B);
-          else store_subtile<SMT_F32, false>(stage, r, lane, p.out, off, B);
-        } else if (p.out_dtype == SMT_BF16) {
-          if (p.accumulate) store_subtile<SMT_BF16, true>(stage, r, lane, p.out, off, B);
-          else store_subtile<SMT_BF16, false>(stage, r, lane, p.out, off, B);
-        } else {
-          if (p.accumulate) store_subtile<SMT_F16, true>(stage, r, lane, p.out, off, B);
-          else store_subtile<SMT_F16, false>(stage, r, lane, p.out, off, B);
-        }
+        const float sv = store_subtile_any(p.out_dtype, acc_out, stage, r, lane, p.out, out0 + cc * 32, B);
+        if (blk == 0) sq0 += sv; else sq1 += sv;
       }
+    }
+    if (p.sq != nullptr) {
+      const float s0 = warp_sum(sq0), s1 = warp_sum(sq1);
+      if (lane == 0) { sq_warp[ew][0] = s0; sq_warp[ew][1] = s1; }
     }
   }
 
@@ -697,6 +739,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) block_grad_umma_2sm_kernel(co
     tc_fence_after();
     tmem_dealloc_2sm(tmem_base, 512);
   }
+  if (p.sq != nullptr && threadIdx.x == 0) {
+    // this CTA stored rows [128 rank, 128 rank + 128) of both blocks: slot `rank` of each; fixed-order sum over the warps
+    float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+    for (int w = 0; w < kEpiWarps; ++w) { t0 += sq_warp[w][0]; t1 += sq_warp[w][1]; }
+    if (it0.sq_slot >= 0) p.sq[it0.sq_slot + (int)rank] = t0;
+    if (has2 && it1.sq_slot >= 0) p.sq[it1.sq_slot + (int)rank] = t1;
+  }
 }
 
 // ---- split-K reduction: G = sum_s partial[s] (fixed order) -----------------------------------------
@@ -705,7 +755,7 @@ template <int ODT>
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, void* __restrict__ out,
                                                             const smt_gemm_item* __restrict__ items,
                                                             int tile_elems, int tiles_per_block, int half_elems,
-                                                            int splits, int64_t n_vec8, int accumulate) {
+                                                            int splits, int64_t n_vec8, int accumulate_all) {
   pdl_wait();  // programmatic dependent launch: the GEMM grid's partial tiles are complete and visible
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t vec = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; vec < n_vec8; vec += stride) {
@@ -721,8 +771,12 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
       acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
     }
     int64_t o = e;
-    if (items != nullptr)
-      o = items[tile / tiles_per_block].out_off + (int64_t)(tile % tiles_per_block) * half_elems + within;
+    int accumulate = accumulate_all;
+    if (items != nullptr) {
+      const smt_gemm_item& item = items[tile / tiles_per_block];
+      o = item.out_off + (int64_t)(tile % tiles_per_block) * half_elems + within;
+      if (item.flags & SMT_ITEM_OVERWRITE) accumulate = 0;
+    }
     if (ODT == SMT_F32) {
       float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + o);
       float4 v0 = make_float4(acc[0], acc[1], acc[2], acc[3]), v1 = make_float4(acc[4], acc[5], acc[6], acc[7]);
@@ -1154,9 +1208,14 @@ extern "C" SMT_API size_t smt_block_grad_gemm_grouped_workspace_bytes(int n_item
   return plan_workspace_bytes(make_plan(n_items, block, T));
 }
 
+extern "C" SMT_API int smt_block_grad_gemm_grouped_emits_sq(int n_items, int block, int64_t T) {
+  if (n_items <= 0 || T <= 0 || !block_ok(block)) return 0;
+  return (use_2sm(n_items, block, T) || make_plan(n_items, block, T).splits == 1) ? 1 : 0;
+}
+
 extern "C" SMT_API int smt_block_grad_gemm_grouped(const void* maps, const smt_gemm_item* items, int n_items,
                                                    int64_t T, int block, int in_dtype, void* out_base,
-                                                   int out_dtype, int accumulate, void* workspace,
+                                                   int out_dtype, int accumulate, float* sq_partials, void* workspace,
                                                    size_t workspace_bytes, void* stream) {
   SMT_CHECK_ARG(n_items >= 0 && T >= 0, "smt_block_grad_gemm_grouped: negative size");
   if (n_items == 0 || T == 0) return SMT_OK;
@@ -1179,6 +1238,7 @@ extern "C" SMT_API int smt_block_grad_gemm_grouped(const void* maps, const smt_g
   gp.out = out_base;
   gp.out_dtype = out_dtype;
   gp.accumulate = accumulate;
+  gp.sq = sq_partials;
   gp.in_fmt = in_dtype == SMT_BF16 ? 1 : 0;
   gp.kt_total = (int)((T + ktile_for(block) - 1) / ktile_for(block));
 

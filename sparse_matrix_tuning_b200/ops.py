@@ -80,6 +80,12 @@ def make_block_table(entries: Sequence[Tuple[torch.Tensor, int, int]], device) -
     for i, (w, r, c) in enumerate(entries):
         if w.dim() != 2 or w.stride(1) != 1:
             raise _lib.SMTLibraryError("block table: weights must be 2-D with unit column stride")
+        if w.data_ptr() % 16 != 0 or (w.stride(0) * w.element_size()) % 16 != 0:
+            # the copy / write-back kernels move 128-bit vectors; a weight re-pointed into a flat buffer at an odd
+            # offset must be rejected here (the C entry points cannot see inside the device-resident table)
+            raise _lib.SMTLibraryError("block table: weight storage must be 16-byte aligned (pointer and row pitch); "
+                                       f"got data_ptr % 16 = {w.data_ptr() % 16}, row pitch = "
+                                       f"{w.stride(0) * w.element_size()} B")
         arr[i].w_ptr = w.data_ptr()
         arr[i].ldw = w.stride(0)
         arr[i].row = int(r)
@@ -367,6 +373,13 @@ def compact_adam(master: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.
         _req(t.dtype == torch.float32 and t.is_contiguous() and t.numel() == grad.numel(),
              "t.dtype == torch.float32 and t.is_contiguous() and t.numel() == grad.numel()")
     _req(grad.is_contiguous(), "grad.is_contiguous()")
+    n_sq = 0
+    if sqnorm is not None:
+        # one scalar (smt_grad_sqnorm) or several partial sums (GEMM epilogue slots, per-chunk norms of a
+        # data-parallel exchange) that the kernel adds up itself in a fixed order
+        _req(sqnorm.dtype == torch.float32 and sqnorm.is_contiguous() and sqnorm.numel() >= 1,
+             "sqnorm.dtype == torch.float32 and sqnorm.is_contiguous() and sqnorm.numel() >= 1")
+        n_sq = sqnorm.numel()
     bc1 = 1.0 - beta1 ** step
     bc2 = 1.0 - beta2 ** step
     _count()
@@ -375,14 +388,52 @@ def compact_adam(master: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.
     with _timed("compact_adam", master.device, grad.numel()):
         check(load().smt_compact_adam(ptr(master), ptr(exp_avg), ptr(exp_avg_sq), ptr(grad), dtype_id(grad.dtype),
                                       grad.numel(), lr, beta1, beta2, eps, weight_decay, bc1, bc2, grad_scale,
-                                      ptr(sqnorm), max_norm, ptr(compact_out), c_dt, ptr(table), n_blocks, block, w_dt,
-                                      _st(master)), "smt_compact_adam")
+                                      ptr(sqnorm), n_sq, max_norm, ptr(compact_out), c_dt, ptr(table), n_blocks, block,
+                                      w_dt, _st(master)), "smt_compact_adam")
 
 
 
 # ---- grouped block-gradient GEMM: several (x, dy) problems in one launch ------------------------------------
 
 LAST_GROUP: dict = {}     # shape of the most recent grouped launch (bench.py reports it)
+HOST_TIME = {"flush_s": 0.0, "flushes": 0}   # host-side cost of building + launching grouped launches (bench.py)
+
+_ITEM_DT = None
+
+
+def _item_dtype():
+    global _ITEM_DT
+    if _ITEM_DT is None:
+        import numpy as np
+        _ITEM_DT = np.dtype([("map_dy", "<u4"), ("map_x", "<u4"), ("row", "<i4"), ("col", "<i4"), ("out_off", "<i8"),
+                             ("flags", "<u4"), ("sq_slot", "<i4")])
+        assert _ITEM_DT.itemsize == C.sizeof(_lib.GemmItem) == 32
+    return _ITEM_DT
+
+
+class _Problem:
+    __slots__ = ("x", "dy", "idx", "idx_id", "out", "block", "accumulate", "sq", "sq_slot0", "sink")
+
+    def __init__(self, x, dy, idx, idx_id, out, block, accumulate, sq, sq_slot0, sink):
+        self.x, self.dy, self.idx, self.idx_id, self.out, self.block = x, dy, idx, idx_id, out, block
+        self.accumulate, self.sq, self.sq_slot0, self.sink = accumulate, sq, sq_slot0, sink
+
+
+_idx_snap: dict = {}      # id(index_list) -> tuple snapshot (validated by value on every use)
+
+
+def _snapshot_index_list(index_list):
+    """Immutable ((row, col), ...) copy of a Python index list; the common case (same list object, same contents as
+    last step) costs one tuple comparison instead of n int() conversions."""
+    key = id(index_list)
+    hit = _idx_snap.get(key)
+    if hit is not None and len(hit) == len(index_list) and tuple(index_list) == hit:
+        return hit
+    snap = tuple((int(r), int(c)) for r, c in index_list)
+    if len(_idx_snap) > 8192:
+        _idx_snap.clear()
+    _idx_snap[key] = snap
+    return snap
 
 
 class BlockGradBatch:
@@ -391,63 +442,83 @@ class BlockGradBatch:
     add() keeps references to the operands; flush() encodes one TMA descriptor per distinct operand on the host,
     ships descriptors + per-block work items with a single pinned H2D copy and launches
     `smt_block_grad_gemm_grouped`.  Problems must share T, the input dtype, the output dtype and the block size
-    (flush() launches one group per distinct combination)."""
+    (flush() launches one group per distinct combination).  The sorted / paired work-item array of a given set of
+    problems is cached, so steady-state steps only re-encode the (pointer-dependent) TMA descriptors."""
 
     def __init__(self):
         self.problems = []
+        self.last_flushed = []
+        self._out_ptrs = set()
+        self._plans: dict = {}
 
     def __len__(self):
         return len(self.problems)
 
-    def add(self, x2d: torch.Tensor, dy2d: torch.Tensor, index_list, out: torch.Tensor, block: int) -> None:
-        require_cuda(x2d, dy2d, out)
+    def n_blocks(self) -> int:
+        return sum(len(pr.idx) for pr in self.problems)
+
+    def add(self, x2d: torch.Tensor, dy2d: torch.Tensor, index_list, out: torch.Tensor, block: int,
+            accumulate: bool = True, sq: Optional[torch.Tensor] = None, sq_slot0: int = -1, sink=None) -> None:
+        """`accumulate=False`: this problem's blocks overwrite `out` (per-item flag) even though the launch as a whole
+        accumulates.  `sq` / `sq_slot0`: fp32 tensor whose slots [sq_slot0 + 2 i, sq_slot0 + 2 i + 1] receive the sum
+        of squares of block i as stored (when the launch shape supports it; `sink.sq_ok` is set accordingly)."""
+        require_cuda(x2d, dy2d, out, sq)
         _req(x2d.dim() == 2 and dy2d.dim() == 2 and x2d.shape[0] == dy2d.shape[0] and x2d.dtype == dy2d.dtype,
              "x2d.dim() == 2 and dy2d.dim() == 2 and x2d.shape[0] == dy2d.shape[0] and x2d.dtype == dy2d.dtype")
         _req(x2d.stride(1) == 1 and dy2d.stride(1) == 1 and out.is_contiguous(),
              "x2d.stride(1) == 1 and dy2d.stride(1) == 1 and out.is_contiguous()")
         _req(out.numel() == len(index_list) * block * block, "out.numel() == len(index_list) * block * block")
-        self.problems.append((x2d, dy2d, [(int(r), int(c)) for r, c in index_list], out, int(block)))
+        if out.data_ptr() in self._out_ptrs:
+            # the same output twice in one launch would race (two tiles read-modify-write the same block)
+            self.flush()
+        self._out_ptrs.add(out.data_ptr())
+        self.problems.append(_Problem(x2d, dy2d, _snapshot_index_list(index_list), id(index_list), out, int(block),
+                                      bool(accumulate), sq, int(sq_slot0), sink))
 
     def flush(self, accumulate: bool = True) -> int:
-        """Launches everything collected so far; returns the number of grouped launches."""
+        """Launches everything collected so far; returns the number of grouped launches.  `last_flushed` keeps the
+        problems of this flush (their sinks have been updated)."""
+        import time
+        t0 = time.perf_counter()
         problems, self.problems = self.problems, []
+        self._out_ptrs = set()
         groups: dict = {}
         for pr in problems:
-            x2d, dy2d, idx, out, block = pr
-            if len(idx) == 0 or x2d.shape[0] == 0:
+            if len(pr.idx) == 0 or pr.x.shape[0] == 0:
                 continue
-            key = (x2d.shape[0], x2d.dtype, out.dtype, block, x2d.device)
+            key = (pr.x.shape[0], pr.x.dtype, pr.out.dtype, pr.block, pr.x.device,
+                   pr.sq.data_ptr() if pr.sq is not None else 0)
             groups.setdefault(key, []).append(pr)
-        for (T, in_dt, out_dt, block, dev), prs in groups.items():
+        for (T, in_dt, out_dt, block, dev, _sq), prs in groups.items():
             self._launch_group(T, in_dt, out_dt, block, dev, prs, accumulate)
+        HOST_TIME["flush_s"] += time.perf_counter() - t0
+        HOST_TIME["flushes"] += 1
+        self.last_flushed = problems
         return len(groups)
 
-    @staticmethod
-    def _launch_group(T, in_dt, out_dt, block, dev, prs, accumulate) -> None:
+    def _items_for(self, T, block, prs, maps_of, base_ptr, esize):
+        """Work-item array for this set of problems (cached: index lists, output offsets and the sharing pattern of
+        the operands do not change from step to step).
+        Work-item order = execution order (CTAs / CTA pairs are dispatched in item order):
+          * within a module, blocks are walked by (block row, block column), and two consecutive blocks of one block
+            row form a PAIR: the cta_group::2 kernel gives items (2c, 2c+1) to CTA pair c and loads the shared dy strip
+            once, so every pair must start at an even position;
+          * a module's unpaired blocks follow its pairs immediately (their strips are still in L2), not at the end of
+            the launch; an odd one out is carried over to the next module to keep the even alignment."""
         import numpy as np
-        lib = load()
-        maps: dict = {}
-
-        def map_index(t: torch.Tensor) -> int:
-            key = (t.data_ptr(), t.shape[1], t.stride(0))
-            if key not in maps:
-                maps[key] = (len(maps), t)
-            return maps[key][0]
-
-        esize = prs[0][3].element_size()
-        base_ptr = min(pr[3].data_ptr() for pr in prs)
-        # Work-item order = execution order (CTAs / CTA pairs are dispatched in item order):
-        #   * within a module, blocks are walked by (block row, block column), and two consecutive blocks of one block
-        #     row form a PAIR: the cta_group::2 kernel gives items (2c, 2c+1) to CTA pair c and loads the shared dy strip
-        #     once, so every pair must start at an even position;
-        #   * a module's unpaired blocks follow its pairs immediately (their strips are still in L2), not at the end of
-        #     the launch; an odd one out is carried over to the next module to keep the even alignment.
+        key = (T, block, tuple((pr.idx, (pr.out.data_ptr() - base_ptr) // esize, pr.accumulate,
+                                pr.sq_slot0 if pr.sq is not None else -1, mx, mdy)
+                               for pr, (mx, mdy) in zip(prs, maps_of)))
+        hit = self._plans.get(key)
+        if hit is not None:
+            return hit
         items, carry = [], []
-        for x2d, dy2d, idx, out, _b in prs:
-            mx, mdy = map_index(x2d), map_index(dy2d)
-            off0 = (out.data_ptr() - base_ptr) // esize
-            entries = [(mdy, mx, r, c, off0 + i * block * block)
-                       for i, (r, c) in sorted(enumerate(idx), key=lambda t: (t[1][0], t[1][1]))]
+        for pr, (mx, mdy) in zip(prs, maps_of):
+            off0 = (pr.out.data_ptr() - base_ptr) // esize
+            flags = 0 if pr.accumulate else _lib.ITEM_OVERWRITE
+            entries = [(mdy, mx, r, c, off0 + i * block * block, flags,
+                        (pr.sq_slot0 + 2 * i) if (pr.sq is not None and pr.sq_slot0 >= 0) else -1)
+                       for i, (r, c) in sorted(enumerate(pr.idx), key=lambda t: (t[1][0], t[1][1]))]
             pairs, singles, i = [], list(carry), 0
             while i < len(entries):
                 if i + 1 < len(entries) and entries[i][2] == entries[i + 1][2]:
@@ -459,25 +530,51 @@ class BlockGradBatch:
             carry = [singles.pop()] if len(singles) % 2 else []
             items += pairs + singles
         items += carry
-        n_items, n_maps = len(items), len(maps)
+        arr = np.array(items, dtype=_item_dtype())
+        n_pairs = sum(1 for k in range(0, len(items) - 1, 2)
+                      if items[k][0] == items[k + 1][0] and items[k][2] == items[k + 1][2])
+        if len(self._plans) > 64:
+            self._plans.clear()
+        self._plans[key] = (arr, n_pairs)
+        return arr, n_pairs
+
+    def _launch_group(self, T, in_dt, out_dt, block, dev, prs, accumulate) -> None:
+        lib = load()
+        maps: dict = {}
+
+        def map_index(t: torch.Tensor) -> int:
+            key = (t.data_ptr(), t.shape[1], t.stride(0))
+            if key not in maps:
+                maps[key] = (len(maps), t)
+            return maps[key][0]
+
+        esize = prs[0].out.element_size()
+        base_ptr = min(pr.out.data_ptr() for pr in prs)
+        maps_of = [(map_index(pr.x), map_index(pr.dy)) for pr in prs]
+        arr, n_pairs = self._items_for(T, block, prs, maps_of, base_ptr, esize)
+        n_items, n_maps = len(arr), len(maps)
+        sq = prs[0].sq
+        emits = bool(sq is not None and lib.smt_block_grad_gemm_grouped_emits_sq(n_items, block, T))
         LAST_GROUP.update(items=n_items, operands=n_maps,
                           cta_group_2=bool(lib.smt_block_grad_gemm_grouped_uses_2sm(n_items, block, T)),
-                          row_sharing_pairs=sum(
-            1 for k in range(0, n_items - 1, 2) if items[k][0] == items[k + 1][0] and items[k][2] == items[k + 1][2]))
-        item_dt = np.dtype([("map_dy", "<u4"), ("map_x", "<u4"), ("row", "<i4"), ("col", "<i4"), ("out_off", "<i8")])
-        nbytes = n_maps * 128 + n_items * item_dt.itemsize
+                          row_sharing_pairs=n_pairs, emits_sq=emits)
+        nbytes = n_maps * 128 + arr.nbytes
         stage = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
         host = stage.numpy()
         in_id = dtype_id(in_dt)
         for _key, (i, t) in maps.items():
             check(lib.smt_encode_operand_map(stage.data_ptr() + i * 128, t.data_ptr(), t.shape[1], T, t.stride(0),
                                              in_id, block), "smt_encode_operand_map")
-        host[n_maps * 128:].view(item_dt)[:] = np.array(items, dtype=item_dt)
+        host[n_maps * 128:] = arr.view("u1").reshape(-1)
         dev_buf = stage.to(dev, non_blocking=True)
         ws_bytes = lib.smt_block_grad_gemm_grouped_workspace_bytes(n_items, block, T)
         ws = _workspace(ws_bytes, dev)
         with _timed("block_grad_gemm", dev, (n_items, block, T)):
             check(lib.smt_block_grad_gemm_grouped(dev_buf.data_ptr(), dev_buf.data_ptr() + n_maps * 128, n_items,
                                                   T, block, in_id, base_ptr, dtype_id(out_dt), 1 if accumulate else 0,
-                                                  ptr(ws), ws_bytes, stream_ptr(dev)), "smt_block_grad_gemm_grouped")
+                                                  ptr(sq) if emits else 0, ptr(ws), ws_bytes, stream_ptr(dev)),
+                  "smt_block_grad_gemm_grouped")
         _count(lib.smt_last_launch_count())
+        for pr in prs:
+            if pr.sink is not None:
+                pr.sink.sq_ok = emits

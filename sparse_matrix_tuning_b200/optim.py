@@ -18,6 +18,17 @@ all-reduces (see dp.py), and `linearZ.backward` writes block gradients straight 
 + one `smt_compact_adam` launch per group then performs: optional 1/world scaling, global-norm clip, AdamW on the
 fp32 masters, rounding to the parameter dtype into `flat_param`, and the write-back of every updated block into
 its dense weight matrix.
+
+Gradient delivery protocol (`GradSink`).  Every `selected_weight` of an arena owns a `GradSink`: the view of
+`flat_grad` that `linearZ.backward` writes into, plus three host-side flags.  `zero_grad()` is LAZY for those
+parameters: it only sets `sink.overwrite`, and the first block-gradient GEMM that delivers afterwards overwrites the
+view instead of accumulating (per-work-item flag) - the 114 MB memset and the read-modify-write of the GEMM epilogue
+disappear from the step.  Further backward passes before the next `step()` accumulate (gradient accumulation).  The
+same epilogue emits the sum of squares of every block it stores (`block_sq`), so the clip norm needs no pass over the
+buffer either; whenever those partial sums cannot be trusted (split-K launches, an all-reduce touched the buffer, a
+gradient was copied in from elsewhere) `step()` falls back to `smt_grad_sqnorm`.  Parameters whose `.grad` was
+dropped or replaced behind the optimizer's back (`model.zero_grad()` sets it to None) are handled: the sink re-attaches
+itself at the next backward and starts from an overwrite; parameters without a sink are copied into the arena.
 """
 from __future__ import annotations
 
@@ -33,6 +44,32 @@ from ._lib import SMTLibraryError
 def _owner_of(p):
     ref = getattr(p, "_smt_owner", None)
     return ref() if ref is not None else None
+
+
+class GradSink:
+    """Where `linearZ.backward` delivers the block gradients of one `selected_weight` in native mode."""
+    __slots__ = ("view", "sq", "sq_slot0", "overwrite", "touched", "sq_ok", "__weakref__")
+
+    def __init__(self, view: torch.Tensor, sq: Optional[torch.Tensor], sq_slot0: int):
+        self.view = view              # [n*b, b] view of the arena's flat_grad
+        self.sq = sq                  # the arena's per-block sum-of-squares slots (2 per block) or None
+        self.sq_slot0 = sq_slot0
+        self.overwrite = False        # the next delivery replaces the contents (lazy zero_grad)
+        self.touched = False          # a gradient was delivered since the last zero_grad
+        self.sq_ok = False            # the slots hold the sum of squares of what the view stores now
+
+    def begin_delivery(self, param) -> bool:
+        """Called by linearZ.backward before it writes.  Returns True when the delivery must ACCUMULATE."""
+        g = param.grad
+        if g is None or g.data_ptr() != self.view.data_ptr():
+            # somebody dropped / replaced .grad (model.zero_grad(set_to_none=True), `p.grad = None`): whatever the
+            # arena still holds is stale - start over and re-attach the view
+            self.overwrite = True
+            param.grad = self.view
+        accumulate = not self.overwrite
+        self.overwrite = False
+        self.touched = True
+        return accumulate
 
 
 class _Arena:
@@ -56,6 +93,14 @@ class _Arena:
         self.exp_avg = torch.zeros(total, dtype=torch.float32, device=self.device)
         self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=self.device)
         self.sqnorm = torch.zeros(1, dtype=torch.float32, device=self.device)
+        # two sum-of-squares slots per selected block (written by the block-gradient GEMM epilogue)
+        n_slots = sum(2 * len(_owner_of(p).index_list) for p in params if _owner_of(p) is not None)
+        self.block_sq = torch.zeros(max(n_slots, 1), dtype=torch.float32, device=self.device)
+        self.sq_dirty = True                                # the buffer was modified by something else (all-reduce, copy)
+        self.sq_override: Optional[torch.Tensor] = None     # partial sums supplied by a data-parallel exchange
+        self.sinks: List[Optional[GradSink]] = []
+        self.grad_views: List[torch.Tensor] = []
+        slot = 0
         for p, off in zip(params, offs):
             n = p.numel()
             view = self.flat_param[off:off + n].view(p.shape)
@@ -66,10 +111,53 @@ class _Arena:
             if p.grad is not None:
                 g.copy_(p.grad)
             p.grad = g
-            if _owner_of(p) is not None:
-                p._smt_grad_sink = g                       # linearZ.backward accumulates here directly
+            self.grad_views.append(g)
+            owner = _owner_of(p)
+            if owner is not None:
+                sink = GradSink(g, self.block_sq, slot)
+                slot += 2 * len(owner.index_list)
+                p._smt_sink = sink                          # linearZ.backward delivers here directly
+                self.sinks.append(sink)
+            else:
+                self.sinks.append(None)
+        self.all_sinks = all(sk is not None for sk in self.sinks)
         self._table = None
         self._table_key = None
+
+    def reconcile_grads(self) -> None:
+        """Before a step: every parameter's gradient must be what the arena holds.
+        * sink parameters that received nothing since zero_grad(): their slice (and slots) become zero;
+        * parameters without a sink (e.g. layer norms in mixture mode) whose `.grad` is no longer the arena view
+          (autograd created a fresh tensor after `set_to_none`): copied in and re-attached; None -> zeros."""
+        for p, view, sink in zip(self.params, self.grad_views, self.sinks):
+            if sink is not None:
+                if p.grad is None or p.grad.data_ptr() != view.data_ptr():
+                    if not sink.touched:                    # dropped and never delivered again: no gradient this step
+                        sink.overwrite = True
+                    p.grad = view
+                if sink.overwrite:                          # nothing was delivered since the (lazy) zero_grad
+                    view.zero_()
+                    n_slots = 2 * (view.numel() // (_owner_of(p).block ** 2))
+                    self.block_sq[sink.sq_slot0:sink.sq_slot0 + n_slots].zero_()
+                    sink.overwrite = False
+                    sink.sq_ok = True
+            else:
+                g = p.grad
+                if g is None:
+                    view.zero_()
+                    self.sq_dirty = True
+                elif g.data_ptr() != view.data_ptr():
+                    view.copy_(g)
+                    self.sq_dirty = True
+                p.grad = view
+
+    def sq_partials(self) -> Optional[torch.Tensor]:
+        """Partial sums of squares that add up to |flat_grad|^2, or None when a full pass is needed."""
+        if self.sq_override is not None:
+            return self.sq_override
+        if self.sq_dirty or not self.all_sinks or not all(sk.sq_ok for sk in self.sinks):
+            return None
+        return self.block_sq
 
     def fused_table(self):
         """One block table covering the whole arena, or None when the group is not purely SMT blocks of one
@@ -119,6 +207,31 @@ class SMTAdam(torch.optim.Optimizer):
         """The flat gradient buffers (one per non-empty group) — what a data-parallel step all-reduces."""
         return [a.flat_grad for a in self._arenas if a is not None]
 
+    def snapshot(self) -> dict:
+        """Deep copy of everything a step changes (flat parameters, fp32 masters and moments, step counters) - lets a
+        harness try a step and take it back (bench.py's data-parallel check)."""
+        snap = {"steps": [g["step"] for g in self.param_groups], "arenas": [], "grad_scale": self.grad_scale}
+        for arena in self._arenas:
+            snap["arenas"].append(None if arena is None else
+                                  tuple(t.clone() for t in (arena.flat_param, arena.master, arena.exp_avg, arena.exp_avg_sq)))
+        return snap
+
+    @torch.no_grad()
+    def restore(self, snap: dict) -> None:
+        self.grad_scale = snap["grad_scale"]
+        for g, st in zip(self.param_groups, snap["steps"]):
+            g["step"] = st
+        for arena, saved in zip(self._arenas, snap["arenas"]):
+            if arena is None:
+                continue
+            for dst, src in zip((arena.flat_param, arena.master, arena.exp_avg, arena.exp_avg_sq), saved):
+                dst.copy_(src)
+            for p in arena.params:
+                owner = _owner_of(p)
+                if owner is not None:
+                    owner.sync_weight(force=True)            # dense blocks <- restored compact values
+                    owner.mark_synced()
+
     def trainable_elements(self) -> int:
         return sum(p.numel() for g in self.param_groups for p in g["params"] if p.requires_grad)
 
@@ -162,10 +275,19 @@ class SMTAdam(torch.optim.Optimizer):
                     mine[name] = val
 
     def zero_grad(self, set_to_none: bool = False):
-        """Zeroes the flat gradient buffers in place (the views stay attached, so nothing is re-pointed)."""
+        """Arena groups: `.grad` views stay attached (nothing is re-pointed).  Parameters fed by `linearZ.backward`
+        are zeroed LAZILY - the next block-gradient launch overwrites them (see the module docstring) - the others
+        are zeroed in place.  Non-arena groups behave like torch's zero_grad."""
         for group, arena in zip(self.param_groups, self._arenas):
             if arena is not None:
-                arena.flat_grad.zero_()
+                arena.sq_override = None
+                arena.sq_dirty = not arena.all_sinks
+                for p, view, sink in zip(arena.params, arena.grad_views, arena.sinks):
+                    if sink is not None:
+                        sink.overwrite, sink.touched, sink.sq_ok = True, False, False
+                    else:
+                        view.zero_()
+                    p.grad = view
             else:
                 for p in group["params"]:
                     if p.grad is not None:
@@ -173,6 +295,13 @@ class SMTAdam(torch.optim.Optimizer):
                             p.grad = None
                         else:
                             p.grad.zero_()
+
+    def mark_grads_modified(self) -> None:
+        """Tell the optimizer that something outside the block-gradient GEMM changed the flat gradient buffers (an
+        all-reduce, a manual edit): the per-block sums of squares are then stale and the clip norm is recomputed."""
+        for arena in self._arenas:
+            if arena is not None:
+                arena.sq_dirty = True
 
     # -- the step --------------------------------------------------------------------------------------
     @torch.no_grad()
@@ -183,19 +312,34 @@ class SMTAdam(torch.optim.Optimizer):
                 loss = closure()
         from .smt.smt import flush_block_grads
         flush_block_grads()                                  # guard: pending grouped block-gradient launches
+        for arena in self._arenas:
+            if arena is not None:
+                arena.reconcile_grads()
         clip = self.max_grad_norm > 0.0
         total_sq = None
+        self.sqnorm_source = None
         if clip:
-            parts = []
-            for group, arena in zip(self.param_groups, self._arenas):
-                if arena is not None:
-                    parts.append(ops.grad_sqnorm(arena.flat_grad, arena.sqnorm))
-                else:
-                    parts += [ops.grad_sqnorm(p.grad.contiguous()) for p in group["params"] if p.grad is not None]
-            if len(parts) == 1:
-                total_sq = parts[0]
-            elif parts:
-                total_sq = torch.stack([t.reshape(()) for t in parts]).sum().reshape(1)
+            live = [a for a in self._arenas if a is not None]
+            loose = any(a is None and any(p.grad is not None for p in g["params"])
+                        for g, a in zip(self.param_groups, self._arenas))
+            partials = live[0].sq_partials() if (len(live) == 1 and not loose) else None
+            if partials is not None:
+                # sums of squares emitted by the GEMM epilogue (or by the data-parallel exchange): no extra pass
+                total_sq = partials
+                self.sqnorm_source = "partials"
+            else:
+                parts = []
+                for group, arena in zip(self.param_groups, self._arenas):
+                    if arena is not None:
+                        parts.append(ops.grad_sqnorm(arena.flat_grad, arena.sqnorm))
+                    else:
+                        parts += [ops.grad_sqnorm(p.grad.contiguous()) for p in group["params"] if p.grad is not None]
+                if len(parts) == 1:
+                    total_sq = parts[0]
+                elif parts:
+                    total_sq = torch.stack([t.reshape(()) for t in parts]).sum().reshape(1)
+                self.sqnorm_source = "grad_sqnorm"
+        self.last_sqnorm = total_sq                          # tensor(s) the clip used (tests / reports)
         for group, arena in zip(self.param_groups, self._arenas):
             group["step"] += 1
             b1, b2 = group["betas"]
@@ -208,6 +352,13 @@ class SMTAdam(torch.optim.Optimizer):
                 for p in group["params"]:
                     if p.grad is not None:
                         self._step_loose(p, common)
+        for arena in self._arenas:
+            if arena is not None:                            # the step consumed this gradient state
+                arena.sq_override = None
+                arena.sq_dirty = True
+                for sink in arena.sinks:
+                    if sink is not None:
+                        sink.touched = False
         return loss
 
     def _step_arena(self, arena: _Arena, common) -> None:

@@ -13,9 +13,11 @@ Public names kept identical to what the reference driver imports (fine_tune.py:3
 
 What changed underneath:
   * `__init__` gathers all selected blocks with ONE kernel launch (`smt_block_gather`) instead of n slice copies;
-  * `forward` scatters compact -> dense with ONE launch and only when `selected_weight` changed since the last
-    scatter (the reference re-scatters n slices on every forward, twice per step under checkpointing);
-    when the fused optimizer (`SMTAdam`) wrote the blocks itself, nothing is launched at all;
+  * `forward` scatters compact -> dense with ONE launch on every call, exactly when the reference does
+    (smt.py:332-341; it issues n slice copies).  The only case in which the launch is skipped is when the fused
+    optimizer (`SMTAdam`) has itself written the updated blocks into the dense weight and says so (`mark_synced`);
+    any optimizer that updates `selected_weight` behind our back (DeepSpeed FusedAdam through `p.data`, ZeRO flat
+    partitions) therefore always sees its update in the next forward;
   * `linearZ.backward` forms every selected block gradient in ONE grouped tcgen05/TMEM GEMM
     (`smt_block_grad_gemm`): fp32 accumulation over all B*S tokens, rounded once — the reference does a bmm, a
     batch reduction and a slice copy per block, rounding to bf16 per batch entry;
@@ -28,6 +30,7 @@ fails for every non-square weight.  Its gradient fo
 """
 from __future__ import annotations
 
+import contextlib
 import re
 import threading
 import weakref
@@ -113,34 +116,67 @@ def _block_rc_for(index_list, device) -> torch.Tensor:
 # `loss.backward()` returns.  Per-module launches of ~9-30 blocks cannot fill 148 SMs; the grouped launch of all
 # 869 blocks can.  `flush_block_grads()` is also called by SMTAdam.step() / dp.allreduce_compact_grads as a guard.
 
-_grouped = {"enabled": False}
+_grouped = {"enabled": False, "chunk_blocks": 0}
 _pending = ops.BlockGradBatch()
 _pending_lock = threading.Lock()
-_pending_state = {"callback_queued": False, "stream": None}
+_pending_state = {"callback_queued": False, "stream": None, "last_x": None}
+_flush_listeners = []
 
 
-def set_grouped_backward(enabled: bool) -> None:
-    """Enable / disable deferral of the block-gradient GEMMs to one grouped launch per backward pass."""
+def set_grouped_backward(enabled: bool, chunk_blocks: int = 0) -> None:
+    """Enable / disable deferral of the block-gradient GEMMs to grouped launches.
+
+    chunk_blocks = 0: ONE launch per backward pass (when the autograd engine finishes).
+    chunk_blocks > 0: additionally flush DURING the backward pass, at a layer boundary (a module with a different
+    input arrives), whenever at least that many blocks are pending - each chunk still fills the GPU (choose >= 148
+    tiles) and a data-parallel exchange can all-reduce it while the rest of the backward pass runs (dp.py)."""
     flush_block_grads()
     _grouped["enabled"] = bool(enabled)
+    _grouped["chunk_blocks"] = int(chunk_blocks) if enabled else 0
+
+
+def add_flush_listener(fn) -> None:
+    """`fn(sinks)` is called after every grouped launch with the GradSinks it delivered to (on the thread and the
+    stream that launched it)."""
+    if fn not in _flush_listeners:
+        _flush_listeners.append(fn)
+
+
+def remove_flush_listener(fn) -> None:
+    if fn in _flush_listeners:
+        _flush_listeners.remove(fn)
+
+
+def _flush_locked() -> int:
+    if len(_pending) == 0:
+        return 0
+    stream = _pending_state["stream"]
+    ctx = torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()
+    with ctx:
+        launches = _pending.flush(accumulate=True)
+        sinks = [pr.sink for pr in _pending.last_flushed if pr.sink is not None]
+        for fn in list(_flush_listeners):
+            fn(sinks)
+    return launches
 
 
 def flush_block_grads() -> int:
     """Run every pending block-gradient problem now (no-op when nothing is pending)."""
     with _pending_lock:
         _pending_state["callback_queued"] = False
-        if len(_pending) == 0:
-            return 0
-        stream = _pending_state["stream"]
-        if stream is not None:
-            with torch.cuda.stream(stream):
-                return _pending.flush(accumulate=True)
-        return _pending.flush(accumulate=True)
+        _pending_state["last_x"] = None
+        return _flush_locked()
 
 
-def _enqueue_block_grad(x2, dy2, index_list, sink, block) -> None:
+def _enqueue_block_grad(x2, dy2, index_list, sink, block, accumulate) -> None:
     with _pending_lock:
-        _pending.add(x2, dy2, index_list, sink, block)
+        chunk = _grouped["chunk_blocks"]
+        xkey = (x2.data_ptr(), x2.shape[0])
+        if chunk > 0 and _pending_state["last_x"] not in (None, xkey) and _pending.n_blocks() >= chunk:
+            _flush_locked()                                     # layer boundary with a GPU-filling chunk pending
+        _pending_state["last_x"] = xkey
+        _pending.add(x2, dy2, index_list, sink.view, block, accumulate=accumulate, sq=sink.sq, sq_slot0=sink.sq_slot0,
+                     sink=sink)
         _pending_state["stream"] = torch.cuda.current_stream(x2.device)
         if not _pending_state["callback_queued"]:
             _pending_state["callback_queued"] = True
@@ -178,13 +214,16 @@ class linearZ(torch.autograd.Function):
             if x2.dtype != dy2.dtype:
                 x2 = x2.to(dy2.dtype)
             rc = _block_rc_for(ctx.index_list, dy2.device)
-            sink = getattr(ctx.sw_ref, "_smt_grad_sink", None)
+            sink = getattr(ctx.sw_ref, "_smt_sink", None)
             if sink is not None:
-                # native mode: accumulate straight into the flat (NCCL) gradient buffer, nothing returned
+                # native mode: deliver straight into the flat (NCCL) gradient buffer, nothing returned.  The sink says
+                # whether this delivery accumulates or overwrites (first one after a lazy zero_grad).
+                accumulate = sink.begin_delivery(ctx.sw_ref)
                 if _grouped["enabled"] and dy2.dtype != torch.float32 and n > 0:
-                    _enqueue_block_grad(x2, dy2, ctx.index_list, sink, b)      # one grouped launch per backward
+                    _enqueue_block_grad(x2, dy2, ctx.index_list, sink, b, accumulate)   # grouped launch(es) per backward
                 else:
-                    ops.block_grad_gemm(x2, dy2, rc, b, out=sink, accumulate=True)
+                    ops.block_grad_gemm(x2, dy2, rc, b, out=sink.view, accumulate=accumulate)
+                    sink.sq_ok = False
             else:
                 grad_weight = ops.block_grad_gemm(x2, dy2, rc, b, out_dtype=grad_output.dtype)  # smt.py:382-404
                 grad_weight = grad_weight.view(n * b, b)
@@ -220,8 +259,9 @@ class LinearLayer_MatrixSparsity(nn.Module):
         self.selected_weight = nn.Parameter(compact, requires_grad=True)
         self.selected_weight._smt_owner = weakref.ref(self)   # lets SMTAdam find the dense weight to write back
         self.fn = linearZ.apply
-        # (storage pointer, version) of selected_weight at the last compact -> dense write-back
-        self._synced = (self.selected_weight.data_ptr(), self.selected_weight._version)
+        # Set ONLY by `mark_synced()` (= SMTAdam after its fused write-back): (storage pointer, version) of
+        # selected_weight at that moment.  None = "nobody vouches for the dense weight": scatter on every forward.
+        self._synced = None
 
     # -- device table of (W pointer, ld, row, col) per block, rebuilt if the weight storage moves --
     def _block_table(self) -> torch.Tensor:
@@ -239,20 +279,26 @@ class LinearLayer_MatrixSparsity(nn.Module):
         return out
 
     def mark_synced(self) -> None:
-        """Called by the fused optimizer after it has written the updated blocks into `weight` itself."""
+        """Called by the fused optimizer (SMTAdam) right after it has written the updated blocks into `weight`
+        itself.  The mark is tied to the parameter's storage pointer and version counter: re-pointing `.data`
+        (DeepSpeed / ZeRO flat buffers) or any version-counted write to the Parameter invalidates it.  Writes
+        through `selected_weight.data` are invisible to the version counter, so whoever does that while SMTAdam
+        owns the parameter must call `sync_weight(force=True)`; without SMTAdam nothing is ever skipped."""
         self._synced = (self.selected_weight.data_ptr(), self.selected_weight._version)
 
     def sync_weight(self, force: bool = False) -> None:
-        """compact -> dense write-back (smt.py:332-341) — one launch, skipped when nothing changed."""
-        state = (self.selected_weight.data_ptr(), self.selected_weight._version)
-        if force or self._synced != state:
-            n = len(self.index_list)
-            if n:
-                sw = self.selected_weight.data
-                if sw.dtype != self.weight.dtype:
-                    sw = sw.to(self.weight.dtype)
-                ops.block_scatter(self._block_table(), n, self.block, sw.contiguous())
-            self._synced = state
+        """compact -> dense write-back (smt.py:332-341): ONE launch per call.  Unconditional like the reference's
+        loop, except right after an SMTAdam step that wrote the dense blocks itself (see `mark_synced`)."""
+        if not force and self._synced is not None and \
+                self._synced == (self.selected_weight.data_ptr(), self.selected_weight._version):
+            return
+        self._synced = None
+        n = len(self.index_list)
+        if n:
+            sw = self.selected_weight.data
+            if sw.dtype != self.weight.dtype:
+                sw = sw.to(self.weight.dtype)
+            ops.block_scatter(self._block_table(), n, self.block, sw.contiguous())
 
     def forward(self, x):
         self.sync_weight()
@@ -469,24 +515,16 @@ class LinearLayer_ChannelSparsity(nn.Module):
             ops.column_gather(weight.data, _channel_idx_for(index_list, weight.device), compact)
         self.selected_weight = nn.Parameter(compact, requires_grad=True)
         self.fn = linearChannel.apply
-        self._synced = (self.selected_weight.data_ptr(), self.selected_weight._version)
-
-    def _apply(self, fn, *args, **kwargs):
-        out = super()._apply(fn, *args, **kwargs)
-        self._synced = None
-        return out
 
     def sync_weight(self, force: bool = False) -> None:
-        """compact -> dense write-back (smt.py:208-211) — one launch, skipped when nothing changed."""
-        state = (self.selected_weight.data_ptr(), self.selected_weight._version)
-        if force or self._synced != state:
-            if len(self.index_list):
-                sw = self.selected_weight.data
-                if sw.dtype != self.weight.dtype:
-                    sw = sw.to(self.weight.dtype)
-                ops.column_scatter(self.weight.data, _channel_idx_for(self.index_list, self.weight.device),
-                                   sw.contiguous())
-            self._synced = state
+        """compact -> dense write-back (smt.py:208-211): one launch on EVERY forward, like the reference's loop —
+        whatever optimizer updated `selected_weight` (also through `.data` or an aliased flat buffer) is seen."""
+        if len(self.index_list):
+            sw = self.selected_weight.data
+            if sw.dtype != self.weight.dtype:
+                sw = sw.to(self.weight.dtype)
+            ops.column_scatter(self.weight.data, _channel_idx_for(self.index_list, self.weight.device),
+                               sw.contiguous())
 
     def forward(self, x):
         self.sync_weight()

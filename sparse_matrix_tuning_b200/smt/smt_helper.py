@@ -8,6 +8,9 @@ fine_tune.py:40):
     get_blocks                        smt_helper.py:272-294
     get_named_linears                 smt_helper.py:297-302
 
+plus, as callable helpers, the budget arithmetic the reference driver does inline (fine_tune.py:217-241):
+`targeted_module_dims(model)`, `num_total_blocks(model)`, `block_budget(model, ratio)`.
+
 Differences from the reference, all deliberate:
   * scoring and top-k run on the GPU through the C-ABI (`smt_block_score_reduce`, `smt_topk_blocks`); the
     Python heap with one `.item()` per block is gone.  Selected indices are bit-exact for identical scores,
@@ -209,6 +212,42 @@ def select_channel_based_on_activation(activation,
     """Reference: smt_helper.py:149-230. Returns defaultdict(list) {(module, layer): [channel, ...]}."""
     keys, scores = channel_scores_on_device(activation, calculate_strategy)
     return _select_from_device_scores(keys, scores, n, selection_strategy, lambda ki, lo: lo)
+
+
+# ---- block budget (the driver-side arithmetic of fine_tune.py:217-241, as callable helpers) ---------------------------
+
+_TARGETED_MODULE_NAMES = ("gate_proj", "up_proj", "down_proj", "q_proj", "k_proj", "v_proj")    # fine_tune.py:217-220
+
+
+def targeted_module_dims(model) -> Dict[str, List[int]]:
+    """{module kind: [rows, cols]} of the FIRST parameter whose name contains 'weight' and the kind - fine_tune.py:221-228
+    (the dict `select_submatrix_based_on_grads` takes as its second argument)."""
+    dims: Dict[str, List[int]] = {}
+    for name, p in model.named_parameters():
+        if "weight" not in name:
+            continue
+        for kind in _TARGETED_MODULE_NAMES:
+            if kind in name and kind not in dims:
+                dims[kind] = [int(p.shape[0]), int(p.shape[1])]
+                break
+    return dims
+
+
+def num_total_blocks(model, block: int = None) -> float:
+    """fine_tune.py:231-234: sum over EVERY 2-D parameter (embeddings and lm_head included) of rows/b * cols/b, with
+    the reference's float division (a matrix whose sides are not multiples of b contributes a fraction)."""
+    b = Block_dimension if block is None else block
+    total = 0.0
+    for _name, p in model.named_parameters():
+        if p.ndim == 2:
+            total += p.shape[0] / b * p.shape[1] / b
+    return total
+
+
+def block_budget(model, ratio: float, block: int = None) -> int:
+    """Number of blocks a `--downsample_*_blocks_ratio` flag buys: int(ratio * num_total_blocks) - fine_tune.py:236,239
+    (truncation, not rounding).  LLaMA-3-8B: 122 528 blocks -> 0.0071 buys 869."""
+    return int(ratio * num_total_blocks(model, block))
 
 
 def get_blocks(model):

@@ -100,7 +100,10 @@ def test_linear_layer_matrix_sparsity_golden(api, case):
     del w2
 
 
-def test_forward_rescatters_only_when_selected_weight_changed(api):
+def test_forward_always_rescatters_without_the_fused_optimizer(api):
+    """Reference semantics (smt.py:332-341): EVERY forward writes selected_weight into the dense weight.  Updates that
+    bypass the Parameter's version counter - `p.data.add_()` (what DeepSpeed's FusedAdam does) or a write through a flat
+    buffer that `p.data` aliases (BF16_Optimizer / ZeRO partitions) - must be visible in the next forward."""
     M, _H = api
     torch.manual_seed(0)
     w = torch.nn.Parameter(torch.randn(512, 512, device="cuda").bfloat16())
@@ -108,12 +111,67 @@ def test_forward_rescatters_only_when_selected_weight_changed(api):
     x = torch.randn(1, 8, 512, device="cuda").bfloat16()
     y0 = layer(x)
     w.data[0:256, 256:512] = 7.0                       # corrupt a selected block behind the module's back
-    y1 = layer(x)                                      # selected_weight unchanged => no scatter => corruption visible
-    assert not torch.equal(y0, y1)
-    with torch.no_grad():
-        layer.selected_weight.add_(0.0)                # any in-place write bumps the version => scatter restores W
+    assert torch.equal(layer(x), y0)                   # the forward's scatter repairs it, like the reference's loop
+    # (1) in-place update through .data: version counter does not move
+    v0 = layer.selected_weight._version
+    layer.selected_weight.data.add_(1.0)
+    assert layer.selected_weight._version == v0
+    y1 = layer(x)
+    want = O.gather_blocks(w.detach().cpu(), layer.index_list, 256)
+    assert torch.equal(want, layer.selected_weight.detach().cpu())          # dense weight now holds the update
+    assert not torch.equal(y1, y0)
+    # (2) .data re-pointed into a flat buffer, then the flat buffer is written (no version bump, same data_ptr)
+    flat = torch.zeros(layer.selected_weight.numel() + 64, dtype=torch.bfloat16, device="cuda")
+    view = flat[64:].view_as(layer.selected_weight)
+    view.copy_(layer.selected_weight.data)
+    layer.selected_weight.data = view
+    flat.mul_(0.5)
     y2 = layer(x)
-    assert torch.equal(y0, y2)
+    assert torch.equal(O.gather_blocks(w.detach().cpu(), layer.index_list, 256), layer.selected_weight.detach().cpu())
+    assert not torch.equal(y2, y1)
+    # the channel-sparsity twin follows the same rule
+    wc = torch.nn.Parameter(torch.randn(256, 512, device="cuda").bfloat16())
+    ch = M.LinearLayer_ChannelSparsity(wc, index_list=[3, 500, 17])
+    ch(x)
+    ch.selected_weight.data.add_(1.0)
+    ch(x)
+    assert torch.equal(wc.detach()[:, [3, 500, 17]].t().contiguous(), ch.selected_weight.detach())
+
+
+def test_fused_optimizer_skips_the_scatter_only_while_it_vouches_for_the_weight(api):
+    """Under SMTAdam the dense blocks are written by the Adam kernel, so forward launches nothing - until anything
+    invalidates that: a version-counted write to the Parameter, or `.data` being re-pointed elsewhere."""
+    M, _H = api
+    from sparse_matrix_tuning_b200 import ops
+    from sparse_matrix_tuning_b200.optim import SMTAdam
+    torch.manual_seed(1)
+    w = torch.nn.Parameter(torch.randn(512, 512, device="cuda").bfloat16() * 0.05)
+    layer = M.LinearLayer_MatrixSparsity(w, index_list=[(0, 1), (1, 0)])
+    opt = SMTAdam([layer.selected_weight], lr=1e-2)
+    x = torch.randn(2, 16, 512, device="cuda").bfloat16()
+    opt.zero_grad()
+    layer(x).float().pow(2).mean().backward()
+    opt.step()
+    assert torch.equal(O.gather_blocks(w.detach().cpu(), layer.index_list, 256), layer.selected_weight.detach().cpu())
+    n0 = ops.LAUNCHES["total"]
+    with torch.no_grad():
+        layer(x)
+        layer(x)
+    assert ops.LAUNCHES["total"] == n0                 # no scatter launched: SMTAdam vouches for the dense weight
+    with torch.no_grad():
+        layer.selected_weight.mul_(2.0)                # version-counted write => mark invalid => scatter again
+        layer(x)
+    assert ops.LAUNCHES["total"] == n0 + 1
+    assert torch.equal(O.gather_blocks(w.detach().cpu(), layer.index_list, 256), layer.selected_weight.detach().cpu())
+    opt.zero_grad()
+    layer(x).float().pow(2).mean().backward()
+    opt.step()
+    layer.selected_weight.data = layer.selected_weight.data.clone() * 3   # re-pointed storage => invalid
+    n1 = ops.LAUNCHES["total"]
+    with torch.no_grad():
+        layer(x)
+    assert ops.LAUNCHES["total"] == n1 + 1
+    assert torch.equal(O.gather_blocks(w.detach().cpu(), layer.index_list, 256), layer.selected_weight.detach().cpu())
 
 
 def test_convert_back_merges_blocks(api):
@@ -368,8 +426,61 @@ def test_gradient_accumulation_over_micro_batches(api):
     got = layer.selected_weight.grad.float()
     assert layer.selected_weight.grad.data_ptr() == opt.flat_grads()[0].data_ptr()   # .grad IS the flat (NCCL) buffer
     assert (got - want).abs().max().item() <= 2 ** -6 * want.abs().max().item()
+    # zero_grad() is lazy for block parameters: the next delivery OVERWRITES (no memset, no read-modify-write) ...
     opt.zero_grad()
+    layer(xs[0]).backward(gs[0])
+    want0 = gs[0].reshape(-1, 256).float().t() @ xs[0].reshape(-1, 512).float()[:, 256:512]
+    assert (layer.selected_weight.grad.float() - want0).abs().max().item() <= 2 ** -7 * want0.abs().max().item()
+    # ... and a step that received no gradient at all sees zeros, not last step's values
+    opt.step()
+    before = opt.state[layer.selected_weight]["master"].clone()
+    m_before = opt.state[layer.selected_weight]["exp_avg"].clone()
+    opt.zero_grad()
+    opt.step()
     assert not opt.flat_grads()[0].any()
+    assert torch.allclose(opt.state[layer.selected_weight]["exp_avg"], m_before * 0.9)   # g = 0: m <- beta1 * m
+    assert not torch.equal(opt.state[layer.selected_weight]["master"], before)           # momentum still moves p
+
+
+def test_gradients_dropped_behind_the_optimizers_back(api):
+    """`model.zero_grad()` (set_to_none=True by default) and `p.grad = None` detach `.grad` from the flat arena.  The
+    next backward must start from a clean slate (not accumulate onto last step's values) and re-attach the view;
+    parameters that are not fed by linearZ (e.g. layer norms in mixture mode) get their fresh `.grad` copied in."""
+    M, _H = api
+    from sparse_matrix_tuning_b200.optim import SMTAdam
+    torch.manual_seed(9)
+    w = torch.nn.Parameter(torch.randn(256, 512, device="cuda").bfloat16() * 0.05)
+    layer = M.LinearLayer_MatrixSparsity(w, index_list=[(0, 1), (0, 0)])
+    norm_w = torch.nn.Parameter(torch.ones(512, device="cuda").bfloat16())
+    opt = SMTAdam([layer.selected_weight, norm_w], lr=1e-3)
+    x = torch.randn(2, 64, 512, device="cuda").bfloat16()
+    g = torch.randn(2, 64, 256, device="cuda").bfloat16()
+
+    def fwd_bwd():
+        layer(x * norm_w).backward(g)
+
+    def truth():
+        xx = (x * norm_w).reshape(-1, 512).float()
+        full = g.reshape(-1, 256).float().t() @ xx
+        return torch.cat([full[:, 256:512], full[:, 0:256]], 0)
+
+    opt.zero_grad()
+    fwd_bwd()
+    g_norm_1 = norm_w.grad.detach().float().clone()
+    opt.step()
+    for p in (layer.selected_weight, norm_w):          # what HF Trainer / many loops do instead of opt.zero_grad()
+        p.grad = None
+    fwd_bwd()
+    assert layer.selected_weight.grad is not None
+    assert layer.selected_weight.grad.data_ptr() == opt.flat_grads()[0].data_ptr()
+    want = truth()
+    assert (layer.selected_weight.grad.float() - want).abs().max().item() <= 2 ** -7 * want.abs().max().item()
+    assert norm_w.grad.data_ptr() != opt._arenas[0].grad_views[1].data_ptr()       # autograd made a fresh tensor
+    fresh = norm_w.grad.detach().float().clone()
+    opt.step()                                                                     # copies it in and re-attaches
+    assert norm_w.grad.data_ptr() == opt._arenas[0].grad_views[1].data_ptr()
+    assert torch.equal(norm_w.grad.float(), fresh)
+    assert (fresh - g_norm_1).abs().max().item() <= 0.05 * g_norm_1.abs().max().item() + 1e-3   # not doubled
 
 
 def test_smtadam_unflattened_mode_matches_flat_mode(api):

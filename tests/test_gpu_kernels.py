@@ -431,6 +431,97 @@ def test_grouped_gemm_2sm_cta_pairs(ops, monkeypatch, out_dtype, accumulate):
         assert (got - want).abs().max().item() <= tol * want.abs().max().item()
 
 
+@pytest.mark.parametrize("two_sm", [True, False])
+@pytest.mark.parametrize("out_dtype", [torch.bfloat16, torch.float32])
+def test_grouped_gemm_item_overwrite_flags_and_sq_partials(ops, monkeypatch, two_sm, out_dtype):
+    """Work-item v2: (a) a problem added with accumulate=False OVERWRITES its blocks inside an accumulating launch (the
+    lazy zero_grad of SMTAdam), the others accumulate; (b) the epilogue's per-block sums of squares describe exactly
+    what is stored (after accumulation and rounding), are bit-reproducible, and differ between the cta_group::2 and the
+    single-CTA kernel by fp32 summation order only."""
+    torch.manual_seed(21)
+    T, b, P = 448, 256, 4                                             # T < 512 => no split-K => the launch emits sums
+    xs = [torch.randn(T, 1536, device="cuda").bfloat16() for _ in range(P)]
+    dys = [torch.randn(T, 2560, device="cuda").bfloat16() for _ in range(P)]
+    idx = [(r, c) for r in range(10) for c in range(6)][:-7] + [(9, 5)]             # 54 blocks, pairs + singles
+    nblk = len(idx)
+    n = nblk * b * b
+    init = (torch.randn(P * n, device="cuda") * 50).to(out_dtype)
+    overwrite = [True, False, True, False]
+    if not two_sm:
+        monkeypatch.setenv("SMT_GEMM_2SM", "0")
+
+    def run():
+        out = init.clone()
+        sq = torch.full((2 * P * nblk,), -1.0, device="cuda")
+        batch = ops.BlockGradBatch()
+        for i in range(P):
+            batch.add(xs[i], dys[i], idx, out[i * n:(i + 1) * n].view(-1, b), b, accumulate=not overwrite[i],
+                      sq=sq, sq_slot0=2 * i * nblk)
+        batch.flush(accumulate=True)
+        return out, sq
+
+    out, sq = run()
+    assert ops.LAST_GROUP["emits_sq"] and ops.LAST_GROUP["cta_group_2"] == two_sm
+    tol = 2 ** -7 if out_dtype == torch.bfloat16 else 3e-5
+    for i in range(P):
+        ref = dys[i].float().t() @ xs[i].float()
+        want = torch.stack([ref[r * b:(r + 1) * b, c * b:(c + 1) * b] for r, c in idx])
+        if not overwrite[i]:
+            want = want + init[i * n:(i + 1) * n].view(nblk, b, b).float()
+        got = out[i * n:(i + 1) * n].view(nblk, b, b).float()
+        assert (got - want).abs().max().item() <= tol * want.abs().max().item(), i
+    stored = out.view(P * nblk, 2, (b // 2) * b).double()              # halves: rows [0,128) and [128,256) of each block
+    want_sq = (stored ** 2).sum(-1).reshape(-1)
+    assert torch.allclose(sq.double(), want_sq, rtol=1e-5, atol=0)
+    out2, sq2 = run()
+    assert torch.equal(out, out2) and torch.equal(sq, sq2)               # deterministic
+
+
+@pytest.mark.parametrize("block", [64, 128])
+def test_grouped_gemm_sq_partials_small_blocks(ops, block):
+    """b = 64 / 128: one tile per block - slot 0 holds the block's whole sum of squares, slot 1 is written as 0."""
+    torch.manual_seed(block)
+    T = 256
+    x = torch.randn(T, 1024, device="cuda").bfloat16()
+    dy = torch.randn(T, 1024, device="cuda").bfloat16()
+    nb = 1024 // block
+    idx = [(r, c) for r in range(nb) for c in range(nb)]
+    if len(idx) > 200:
+        idx = idx[:200]
+    out = torch.empty(len(idx) * block * block, device="cuda", dtype=torch.bfloat16)
+    sq = torch.full((2 * len(idx),), -1.0, device="cuda")
+    batch = ops.BlockGradBatch()
+    batch.add(x, dy, idx, out.view(-1, block), block, accumulate=False, sq=sq, sq_slot0=0)
+    batch.flush(accumulate=True)
+    if not ops.LAST_GROUP["emits_sq"]:
+        pytest.skip("planner chose split-K for this shape")
+    want = (out.view(len(idx), -1).double() ** 2).sum(-1)
+    assert torch.allclose(sq.view(-1, 2)[:, 0].double(), want, rtol=1e-5, atol=0)
+    assert not sq.view(-1, 2)[:, 1].any()
+
+
+def test_compact_adam_with_partial_sqnorms_bit_exact(ops):
+    """The Adam kernel adds n partial sums of squares itself (fixed order: oracle.partial_sqnorm_total) before forming
+    the clip coefficient; fp32 state stays bit-identical to the numpy restatement."""
+    rng = np.random.RandomState(3)
+    N = 64 * 64 * 5
+    p = (rng.randn(N) * 0.02).astype(np.float32)
+    m = np.zeros(N, np.float32)
+    v = np.zeros(N, np.float32)
+    dp, dm, dv = (torch.from_numpy(a.copy()).cuda() for a in (p, m, v))
+    hp = dict(lr=3e-4, beta1=0.9, beta2=0.95, eps=1e-8, weight_decay=0.0)
+    for step, n_part in ((1, 2), (2, 300), (3, 1738), (4, 256)):
+        g = torch.from_numpy(rng.randn(N).astype(np.float32)).bfloat16()
+        parts = (g.float().view(5, -1) ** 2).sum(-1)
+        parts = (parts.repeat_interleave((n_part + 4) // 5)[:n_part] / ((n_part + 4) // 5)).contiguous()
+        total = O.partial_sqnorm_total(parts.numpy())
+        gscale = O.clip_coef(total, np.float32(0.25), np.float32(1.0))
+        ops.compact_adam(dp, dm, dv, g.cuda(), step=step, grad_scale=0.25, sqnorm=parts.cuda(), max_norm=1.0, **hp)
+        p, m, v = O.adamw_fused_step(p, m, v, g.float().numpy(), step=step, gscale=gscale, **hp)
+        assert np.array_equal(dp.cpu().numpy(), p), f"master differs at step {step} ({n_part} partials)"
+        assert np.array_equal(dm.cpu().numpy(), m) and np.array_equal(dv.cpu().numpy(), v)
+
+
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("block", [64, 128, 256])
 def test_block_grad_gemm_token_count_edges(ops, block, dtype):
