@@ -480,7 +480,7 @@ def test_gradients_dropped_behind_the_optimizers_back(api):
     opt.step()                                                                     # copies it in and re-attaches
     assert norm_w.grad.data_ptr() == opt._arenas[0].grad_views[1].data_ptr()
     assert torch.equal(norm_w.grad.float(), fresh)
-    assert (fresh - g_norm_1).abs().max().item() <= 0.05 * g_norm_1.abs().max().item() + 1e-3   # not doubled
+    assert (fresh - g_norm_1).abs().max().item() <= 0.25 * g_norm_1.abs().max().item()          # one gradient, not two
 
 
 def test_smtadam_unflattened_mode_matches_flat_mode(api):
