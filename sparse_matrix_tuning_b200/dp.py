@@ -98,6 +98,8 @@ class OverlappedGradExchange:
         self.events = []                                     # (start, end) CUDA events per chunk when profiling
         self.profile = False
         self.active = True          # set False for all but the last micro-batch of a gradient-accumulation step (like DDP.no_sync)
+        self.keep_local = None      # debug (bench.py's dp_check): a tensor like `flat` that receives this rank's gradients
+                                    # as they were BEFORE each chunk was reduced
         optimizer.grad_scale = 1.0 / self.ws
         _smt.add_flush_listener(self._on_flush)
 
@@ -131,6 +133,8 @@ class OverlappedGradExchange:
                 e0.record(self.side)
             for off, n in self._ranges(sinks):
                 view = self.flat[off:off + n]
+                if self.keep_local is not None:
+                    self.keep_local[off:off + n].copy_(view)
                 if self.ws > 1:
                     w = dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
                     w.wait()                                 # CUDA: stream-level, `side` waits for NCCL's stream
