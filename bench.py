@@ -63,7 +63,7 @@ def parse_args():
                                                             "config-2 points, score kernels, eager reference)")
     ap.add_argument("--no-group", action="store_true", help="launch the block-gradient GEMM per module instead of grouped")
     ap.add_argument("--no-overlap", action="store_true", help="N>1: one blocking all-reduce after backward (round-1 behaviour)")
-    ap.add_argument("--chunk-blocks", type=int, default=192, help="grouped GEMM flush granularity during backward (N>1)")
+    ap.add_argument("--chunk-blocks", type=int, default=440, help="grouped GEMM flush granularity during backward (N>1)")
     ap.add_argument("--capture-steps", type=int, default=4, help="gradient-capture passes of the warm-up phase")
     return ap.parse_args()
 

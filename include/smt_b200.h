@@ -186,10 +186,14 @@ SMT_API int smt_block_grad_gemm_grouped_uses_2sm(int n_items, int block, int64_t
  * the launches that need no split-K (smt_block_grad_gemm_grouped_emits_sq tells); the sums are deterministic (fixed
  * order inside each CTA) and feed the clip of smt_compact_adam without a separate pass over the gradient buffer. */
 SMT_API int smt_block_grad_gemm_grouped_emits_sq(int n_items, int block, int64_t T);
+/* `ld_out`: row pitch of every output tile in elements; 0 = compact storage (pitch = block).  A larger pitch lets the
+ * tiles of one launch assemble a plain row-major matrix (item (r, c) -> out_off = r*b*ld_out + c*b): the channel-sparsity
+ * gradient `partial_input^T @ grad_output` (smt.py:283-284) runs through this form, with the `dy` operand = the packed
+ * selected input channels [T, n] (TMA zero-fills the columns past n) and the `x` operand = grad_output. */
 SMT_API int smt_block_grad_gemm_grouped(const void* maps, const smt_gemm_item* items, int n_items,
                                         int64_t T, int block, int in_dtype, void* out_base, int out_dtype,
-                                        int accumulate, float* sq_partials, void* workspace, size_t workspace_bytes,
-                                        void* stream);
+                                        int accumulate, int64_t ld_out, float* sq_partials, void* workspace,
+                                        size_t workspace_bytes, void* stream);
 /* debug: register a device buffer of 8*max_ctas uint64; each CTA of smt_block_grad_gemm stamps %globaltimer at its
  * phase boundaries (tools/trace_gemm.py). NULL switches tracing off. Not for production use. */
 SMT_API int smt_debug_set_gemm_trace(void* dev_buf, int max_ctas);

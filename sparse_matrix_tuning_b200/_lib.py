@@ -67,7 +67,7 @@ _SIGNATURES = {
     "smt_block_grad_gemm_grouped_uses_2sm": (C.c_int, [C.c_int, C.c_int, C.c_int64]),
     "smt_block_grad_gemm_grouped_emits_sq": (C.c_int, [C.c_int, C.c_int, C.c_int64]),
     "smt_block_grad_gemm_grouped": (C.c_int, [_P, _P, C.c_int, C.c_int64, C.c_int, C.c_int, _P, C.c_int,
-                                              C.c_int, _P, _P, C.c_size_t, _P]),
+                                              C.c_int, C.c_int64, _P, _P, C.c_size_t, _P]),
     "smt_block_grad_gemm_plan": (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_int, C.POINTER(C.c_int),
                                            C.POINTER(C.c_int)]),
     "smt_grad_sqnorm_workspace_bytes": (C.c_size_t, []),

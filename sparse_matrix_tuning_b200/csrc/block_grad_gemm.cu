@@ -233,6 +233,7 @@ struct GemmParams {
   float* sq;                      // grouped, no split-K: per-block sum-of-squares slots (items[i].sq_slot), or NULL
   int* counters;                  // fused reduction: 2 self-resetting ints per tile (NULL = separate reduce kernel)
   unsigned long long* trace;      // debug (SMT_GEMM_TRACE=1): 8 globaltimer stamps per CTA, else NULL
+  int64_t ld_out;                 // row pitch of an output tile in elements (== block for compact storage)
   int splits;
   int kt_total;                   // number of K tiles = ceil(T / ktile_for(block))
   int kt_per_split;
@@ -336,16 +337,19 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 // final output.  The last CTA to finish resets the two counters, so the buffer is all-zero again at kernel end.
 template <int ODT>
 __device__ __forceinline__ void fused_reduce_slice(const float* __restrict__ part0, int splits, int tile_elems,
-                                                   int e_begin, int e_end, void* out, int64_t out_off, bool acc_out) {
+                                                   int e_begin, int e_end, void* out, int64_t out_off, bool acc_out,
+                                                   int b, int64_t ldo) {
   for (int e = e_begin + (int)threadIdx.x * 8; e < e_end; e += (int)blockDim.x * 8) {
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int sp = 0; sp < splits; ++sp) {
       const float* src = part0 + (int64_t)sp * tile_elems + e;
-      const float4 a = ld_cg_f4(src), b = ld_cg_f4(src + 4);
+      const float4 a = ld_cg_f4(src), b4 = ld_cg_f4(src + 4);
       acc[0] += a.x; acc[1] += a.y; acc[2] += a.z; acc[3] += a.w;
-      acc[4] += b.x; acc[5] += b.y; acc[6] += b.z; acc[7] += b.w;
+      acc[4] += b4.x; acc[5] += b4.y; acc[6] += b4.z; acc[7] += b4.w;
     }
-    const int64_t o = out_off + e;
+    // element e of the (row-major, pitch b) tile lives at row e / b, column e % b of the output (pitch ldo); an
+    // 8-element vector never crosses a row (b is a multiple of 8)
+    const int64_t o = out_off + (int64_t)(e / b) * ldo + (e % b);
     if (acc_out) {
       store4<ODT, true>(out, o, make_float4(acc[0], acc[1], acc[2], acc[3]));
       store4<ODT, true>(out, o + 4, make_float4(acc[4], acc[5], acc[6], acc[7]));
@@ -393,7 +397,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) block_grad_umma_kernel(
     row = item.row; col = item.col;
     map_x = p.maps + item.map_x;
     map_dy = p.maps + item.map_dy;
-    out_off = item.out_off + (int64_t)half * 128 * B;
+    out_off = item.out_off + (int64_t)half * 128 * p.ld_out;
     if (item.flags & SMT_ITEM_OVERWRITE) acc_out = false;
     if (p.sq != nullptr && p.splits == 1) sq_slot = item.sq_slot;
   } else {
@@ -489,7 +493,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) block_grad_umma_kernel(
           if (!final_out) {
             store_subtile<SMT_F32, false>(stage, r, lane, part, off_in_tile, B);
           } else {
-            const float sv = store_subtile_any(p.out_dtype, acc_out, stage, r, lane, p.out, out_off + off_in_tile, B);
+            const int64_t off_out = out_off + (int64_t)(mh * 128 + q * 32) * p.ld_out + cc * 32;
+            const float sv = store_subtile_any(p.out_dtype, acc_out, stage, r, lane, p.out, off_out, (int)p.ld_out);
             if (mh == 0) sq0 += sv; else sq1 += sv;
           }
         }
@@ -544,9 +549,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) block_grad_umma_kernel(
     const int e_begin = split * chunk;
     const int e_end = min(e_begin + chunk, C::TILE_ELEMS);
     const float* part0 = p.ws + (int64_t)tile * p.splits * C::TILE_ELEMS;
-    if (p.out_dtype == SMT_F32) fused_reduce_slice<SMT_F32>(part0, p.splits, C::TILE_ELEMS, e_begin, e_end, p.out, out_off, acc_out);
-    else if (p.out_dtype == SMT_BF16) fused_reduce_slice<SMT_BF16>(part0, p.splits, C::TILE_ELEMS, e_begin, e_end, p.out, out_off, acc_out);
-    else fused_reduce_slice<SMT_F16>(part0, p.splits, C::TILE_ELEMS, e_begin, e_end, p.out, out_off, acc_out);
+    if (p.out_dtype == SMT_F32) fused_reduce_slice<SMT_F32>(part0, p.splits, C::TILE_ELEMS, e_begin, e_end, p.out, out_off, acc_out, B, p.ld_out);
+    else if (p.out_dtype == SMT_BF16) fused_reduce_slice<SMT_BF16>(part0, p.splits, C::TILE_ELEMS, e_begin, e_end, p.out, out_off, acc_out, B, p.ld_out);
+    else fused_reduce_slice<SMT_F16>(part0, p.splits, C::TILE_ELEMS, e_begin, e_end, p.out, out_off, acc_out, B, p.ld_out);
     __syncthreads();
     if (threadIdx.x == 0) {
       SMT_TRACE(6);                                         // slice reduced
@@ -715,14 +720,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) block_grad_umma_2sm_kernel(co
 #pragma unroll 1
     for (int blk = 0; blk < (has2 ? 2 : 1); ++blk) {
       const smt_gemm_item& item = blk == 0 ? it0 : it1;
-      const int64_t out0 = item.out_off + (int64_t)((int)rank * 128 + q * 32) * B;
+      const int64_t out0 = item.out_off + (int64_t)((int)rank * 128 + q * 32) * p.ld_out;
       const bool acc_out = p.accumulate != 0 && !(item.flags & SMT_ITEM_OVERWRITE);
 #pragma unroll 1
       for (int cc = par; cc < B / 32; cc += kEpiWarps / 4) {
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(blk * B + cc * 32), r);
         tmem_ld_wait();
-        const float sv = store_subtile_any(p.out_dtype, acc_out, stage, r, lane, p.out, out0 + cc * 32, B);
+        const float sv = store_subtile_any(p.out_dtype, acc_out, stage, r, lane, p.out, out0 + cc * 32, (int)p.ld_out);
         if (blk == 0) sq0 += sv; else sq1 += sv;
       }
     }
@@ -754,8 +759,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) block_grad_umma_2sm_kernel(co
 template <int ODT>
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, void* __restrict__ out,
                                                             const smt_gemm_item* __restrict__ items,
-                                                            int tile_elems, int tiles_per_block, int half_elems,
-                                                            int splits, int64_t n_vec8, int accumulate_all) {
+                                                            int tile_elems, int tiles_per_block, int block,
+                                                            int64_t ldo, int splits, int64_t n_vec8,
+                                                            int accumulate_all) {
   pdl_wait();  // programmatic dependent launch: the GEMM grid's partial tiles are complete and visible
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t vec = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; vec < n_vec8; vec += stride) {
@@ -774,7 +780,7 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restr
     int accumulate = accumulate_all;
     if (items != nullptr) {
       const smt_gemm_item& item = items[tile / tiles_per_block];
-      o = item.out_off + (int64_t)(tile % tiles_per_block) * half_elems + within;
+      o = item.out_off + ((int64_t)(tile % tiles_per_block) * 128 + within / block) * ldo + within % block;
       if (item.flags & SMT_ITEM_OVERWRITE) accumulate = 0;
     }
     if (ODT == SMT_F32) {
@@ -1015,8 +1021,8 @@ int launch_umma_2sm(const GemmParams& gp, int n_items, cudaStream_t st) {
 }
 
 // split-K reduce, launched with programmatic stream serialization so that its launch overlaps the GEMM
-int launch_reduce(const float* ws, void* out, const smt_gemm_item* items, int block, const Plan& pl, int n_blocks,
-                  int out_dtype, int accumulate, cudaStream_t st) {
+int launch_reduce(const float* ws, void* out, const smt_gemm_item* items, int block, int64_t ldo, const Plan& pl,
+                  int n_blocks, int out_dtype, int accumulate, cudaStream_t st) {
   const int64_t n_out = (int64_t)n_blocks * block * block;
   const int64_t n_vec8 = n_out / 8;
   int64_t want = (n_vec8 + 255) / 256;
@@ -1032,13 +1038,12 @@ int launch_reduce(const float* ws, void* out, const smt_gemm_item* items, int bl
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   const int tpb = pl.tiles / n_blocks;
-  const int half_elems = 128 * block;
   if (out_dtype == SMT_F32)
-    SMT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, splitk_reduce_kernel<SMT_F32>, ws, out, items, pl.tile_elems, tpb, half_elems, pl.splits, n_vec8, accumulate));
+    SMT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, splitk_reduce_kernel<SMT_F32>, ws, out, items, pl.tile_elems, tpb, block, ldo, pl.splits, n_vec8, accumulate));
   else if (out_dtype == SMT_BF16)
-    SMT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, splitk_reduce_kernel<SMT_BF16>, ws, out, items, pl.tile_elems, tpb, half_elems, pl.splits, n_vec8, accumulate));
+    SMT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, splitk_reduce_kernel<SMT_BF16>, ws, out, items, pl.tile_elems, tpb, block, ldo, pl.splits, n_vec8, accumulate));
   else
-    SMT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, splitk_reduce_kernel<SMT_F16>, ws, out, items, pl.tile_elems, tpb, half_elems, pl.splits, n_vec8, accumulate));
+    SMT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, splitk_reduce_kernel<SMT_F16>, ws, out, items, pl.tile_elems, tpb, block, ldo, pl.splits, n_vec8, accumulate));
   return SMT_OK;
 }
 
@@ -1154,12 +1159,13 @@ extern "C" SMT_API int smt_block_grad_gemm(const void* x, int64_t ldx, int in_fe
   gp.kt_per_split = pl.kt_per_split;
   gp.out_dtype = out_dtype;
   gp.accumulate = accumulate;
+  gp.ld_out = block;
   gp.in_fmt = in_dtype == SMT_BF16 ? 1 : 0;
   if (int rc = launch_umma<false>(block, mx, mdy, gp, pl, st)) return rc;
   set_launch_count(1);
   if (pl.splits > 1 && gp.counters == nullptr) {
     set_launch_count(2);
-    return launch_reduce(gp.ws, G, nullptr, block, pl, n_blocks, out_dtype, accumulate, st);
+    return launch_reduce(gp.ws, G, nullptr, block, block, pl, n_blocks, out_dtype, accumulate, st);
   }
   return SMT_OK;
 }
@@ -1215,8 +1221,8 @@ extern "C" SMT_API int smt_block_grad_gemm_grouped_emits_sq(int n_items, int blo
 
 extern "C" SMT_API int smt_block_grad_gemm_grouped(const void* maps, const smt_gemm_item* items, int n_items,
                                                    int64_t T, int block, int in_dtype, void* out_base,
-                                                   int out_dtype, int accumulate, float* sq_partials, void* workspace,
-                                                   size_t workspace_bytes, void* stream) {
+                                                   int out_dtype, int accumulate, int64_t ld_out, float* sq_partials,
+                                                   void* workspace, size_t workspace_bytes, void* stream) {
   SMT_CHECK_ARG(n_items >= 0 && T >= 0, "smt_block_grad_gemm_grouped: negative size");
   if (n_items == 0 || T == 0) return SMT_OK;
   SMT_CHECK_ARG(block_ok(block), "smt_block_grad_gemm_grouped: block size %d not in {64,128,256}", block);
@@ -1226,6 +1232,8 @@ extern "C" SMT_API int smt_block_grad_gemm_grouped(const void* maps, const smt_g
   SMT_CHECK_ARG((reinterpret_cast<uintptr_t>(maps) & 63u) == 0 && aligned16(out_base),
                 "smt_block_grad_gemm_grouped: maps must be 64-byte and out_base 16-byte aligned");
   SMT_CHECK_ARG(T < (1ll << 31) - kMaxKTile, "smt_block_grad_gemm_grouped: T too large");
+  SMT_CHECK_ARG(ld_out == 0 || (ld_out >= block && ld_out % 8 == 0 && ld_out < (1ll << 31)),
+                "smt_block_grad_gemm_grouped: ld_out must be 0 (compact tiles) or a multiple of 8 that is >= block");
   const size_t need_total = smt_block_grad_gemm_grouped_workspace_bytes(n_items, block, T);
   if (need_total > 0 && (workspace == nullptr || workspace_bytes < need_total)) {
     set_error("smt_block_grad_gemm_grouped: workspace too small (%zu < %zu)", workspace_bytes, need_total);
@@ -1239,6 +1247,7 @@ extern "C" SMT_API int smt_block_grad_gemm_grouped(const void* maps, const smt_g
   gp.out_dtype = out_dtype;
   gp.accumulate = accumulate;
   gp.sq = sq_partials;
+  gp.ld_out = ld_out > 0 ? ld_out : block;
   gp.in_fmt = in_dtype == SMT_BF16 ? 1 : 0;
   gp.kt_total = (int)((T + ktile_for(block) - 1) / ktile_for(block));
 
@@ -1264,7 +1273,7 @@ extern "C" SMT_API int smt_block_grad_gemm_grouped(const void* maps, const smt_g
   ++launches;
   if (pl.splits > 1 && gp.counters == nullptr) {
     ++launches;
-    if (int rc = launch_reduce(gp.ws, out_base, gp.items, block, pl, n_items, out_dtype, accumulate, st)) return rc;
+    if (int rc = launch_reduce(gp.ws, out_base, gp.items, block, gp.ld_out, pl, n_items, out_dtype, accumulate, st)) return rc;
   }
   set_launch_count(launches);
   return SMT_OK;

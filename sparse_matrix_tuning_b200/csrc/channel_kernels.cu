@@ -15,7 +15,8 @@ namespace {
 
 constexpr int kTile = 32;
 
-// out[t, i] = x[t, idx[i]]: consecutive threads walk i (coalesced writes; reads stay inside one row of x).
+// out[t, i] = x[t, idx[i]] (0 where idx[i] < 0): consecutive threads walk i (coalesced writes; reads stay inside one
+// row of x).
 template <typename E>
 __global__ void __launch_bounds__(256) channel_gather_kernel(const E* __restrict__ x, int64_t ldx, int64_t T,
                                                              const int32_t* __restrict__ idx, int n,
@@ -24,7 +25,8 @@ __global__ void __launch_bounds__(256) channel_gather_kernel(const E* __restrict
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int64_t t = e / n;
     const int i = (int)(e - t * n);
-    out[e] = x[t * ldx + idx[i]];
+    const int c = idx[i];
+    out[e] = c >= 0 ? x[t * ldx + c] : E(0);      // idx < 0: padding column (keeps the row pitch a multiple of 16 B)
   }
 }
 

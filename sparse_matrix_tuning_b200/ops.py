@@ -240,9 +240,12 @@ def block_scatter(table: torch.Tensor, n_blocks: int, block: int, compact: torch
 
 # ---- channel (input-column) movement ------------------------------------------------------------------------
 
-def make_channel_idx(index_list, device) -> torch.Tensor:
-    """int32 device copy of a channel index list."""
-    return torch.tensor([int(i) for i in index_list], dtype=torch.int32, device="cpu").to(device)
+def make_channel_idx(index_list, device, pad_to: int = 1) -> torch.Tensor:
+    """int32 device copy of a channel index list, optionally padded with -1 ("no channel": channel_gather writes a zero
+    column there) to a multiple of `pad_to`."""
+    idx = [int(i) for i in index_list]
+    idx += [-1] * (-len(idx) % pad_to)
+    return torch.tensor(idx, dtype=torch.int32, device="cpu").to(device)
 
 
 def channel_gather(x2: torch.Tensor, idx: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -286,6 +289,58 @@ def column_scatter(W: torch.Tensor, idx: torch.Tensor, compact: torch.Tensor) ->
 # ---- block-gradient GEMM --------------------------------------------------------------------------------
 
 _ws_cache: dict = {}
+_channel_items: dict = {}
+
+
+def channel_grad_gemm(partial: torch.Tensor, n: int, dy2d: torch.Tensor) -> torch.Tensor:
+    """grad[i, o] = sum_t partial[t, i] * dy[t, o] for the n selected input channels - the weight gradient of
+    linearChannel.backward (smt.py:283-284: `partial_input^T @ grad_output`, summed over the batch) on the tcgen05
+    block-gradient pipeline: the packed channels play the `dy` operand (their row blocks are padded by TMA zero fill),
+    grad_output the `x` operand, and every (row block, column block) tile is stored with the row pitch of the result, so
+    the tiles assemble the row-major [n, out_features] gradient directly.  fp32 accumulation over all tokens, ONE
+    rounding.  `partial`: [T, n8] (n8 >= n, row pitch a multiple of 16 bytes, columns >= n zero); returns [n, out]."""
+    require_cuda(partial, dy2d)
+    _req(partial.dim() == 2 and dy2d.dim() == 2 and partial.shape[0] == dy2d.shape[0] and partial.dtype == dy2d.dtype,
+         "partial.dim() == 2 and dy2d.dim() == 2 and partial.shape[0] == dy2d.shape[0] and partial.dtype == dy2d.dtype")
+    _req(partial.stride(1) == 1 and dy2d.stride(1) == 1 and partial.dtype in (torch.bfloat16, torch.float16),
+         "partial.stride(1) == 1 and dy2d.stride(1) == 1 and partial.dtype in (torch.bfloat16, torch.float16)")
+    T, out_f = dy2d.shape
+    _req(0 < n <= partial.shape[1] and (partial.stride(0) * 2) % 16 == 0 and (dy2d.stride(0) * 2) % 16 == 0,
+         "0 < n <= partial.shape[1] and 16-byte row pitches")
+    _req(out_f % 64 == 0, "out_features % 64 == 0")
+    block = 128 if (out_f % 128 == 0 and n > 64) else 64
+    rows, cols = (n + block - 1) // block, out_f // block
+    dev = dy2d.device
+    out = torch.empty(rows * block, out_f, dtype=dy2d.dtype, device=dev)
+    if T == 0:
+        return out.zero_()[:n]
+    import numpy as np
+    key = (rows, cols, block, out_f)
+    arr = _channel_items.get(key)
+    if arr is None:
+        arr = np.array([(0, 1, r, c, r * block * out_f + c * block, _lib.ITEM_OVERWRITE, -1)
+                        for r in range(rows) for c in range(cols)], dtype=_item_dtype())
+        if len(_channel_items) > 64:
+            _channel_items.clear()
+        _channel_items[key] = arr
+    lib = load()
+    n_items = len(arr)
+    stage = torch.empty(2 * 128 + arr.nbytes, dtype=torch.uint8, pin_memory=True)
+    in_id = dtype_id(dy2d.dtype)
+    check(lib.smt_encode_operand_map(stage.data_ptr(), partial.data_ptr(), partial.shape[1], T, partial.stride(0),
+                                     in_id, block), "smt_encode_operand_map")
+    check(lib.smt_encode_operand_map(stage.data_ptr() + 128, dy2d.data_ptr(), out_f, T, dy2d.stride(0), in_id, block),
+          "smt_encode_operand_map")
+    stage.numpy()[256:] = arr.view("u1").reshape(-1)
+    dev_buf = stage.to(dev, non_blocking=True)
+    ws_bytes = lib.smt_block_grad_gemm_grouped_workspace_bytes(n_items, block, T)
+    ws = _workspace(ws_bytes, dev)
+    with _timed("channel_grad_gemm", dev, (n, out_f, T)):
+        check(lib.smt_block_grad_gemm_grouped(dev_buf.data_ptr(), dev_buf.data_ptr() + 256, n_items, T, block, in_id,
+                                              out.data_ptr(), dtype_id(out.dtype), 0, out_f, 0, ptr(ws), ws_bytes,
+                                              stream_ptr(dev)), "smt_block_grad_gemm_grouped")
+    _count(lib.smt_last_launch_count())
+    return out[:n]
 
 
 def _workspace(nbytes: int, device, tag: str = "gemm") -> Optional[torch.Tensor]:
@@ -572,7 +627,7 @@ class BlockGradBatch:
         with _timed("block_grad_gemm", dev, (n_items, block, T)):
             check(lib.smt_block_grad_gemm_grouped(dev_buf.data_ptr(), dev_buf.data_ptr() + n_maps * 128, n_items,
                                                   T, block, in_id, base_ptr, dtype_id(out_dt), 1 if accumulate else 0,
-                                                  ptr(sq) if emits else 0, ptr(ws), ws_bytes, stream_ptr(dev)),
+                                                  0, ptr(sq) if emits else 0, ptr(ws), ws_bytes, stream_ptr(dev)),
                   "smt_block_grad_gemm_grouped")
         _count(lib.smt_last_launch_count())
         for pr in prs:

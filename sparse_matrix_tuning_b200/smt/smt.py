@@ -445,13 +445,15 @@ def get_optimizer_qk_augment_grouped_parameters(
 _idx_cache: Dict[Tuple[int, torch.device], Tuple[tuple, torch.Tensor]] = {}
 
 
-def _channel_idx_for(index_list, device) -> torch.Tensor:
+def _channel_idx_for(index_list, device, pad_to: int = 1) -> torch.Tensor:
+    """int32 device copy of a channel index list (cached per list object, validated by value); `pad_to` > 1 appends -1
+    entries ("zero column") up to a multiple of it."""
     snap = tuple(int(i) for i in index_list)
-    key = (id(index_list), device)
+    key = (id(index_list), device, pad_to)
     hit = _idx_cache.get(key)
     if hit is not None and hit[0] == snap:
         return hit[1]
-    t = ops.make_channel_idx(snap, device)
+    t = ops.make_channel_idx(snap, device, pad_to)
     if len(_idx_cache) > 4096:
         _idx_cache.clear()
     _idx_cache[key] = (snap, t)
@@ -470,8 +472,12 @@ class linearChannel(torch.autograd.Function):
         x2 = input.reshape(-1, input.shape[-1])
         if x2.stride(-1) != 1:
             x2 = x2.contiguous()
-        idx = _channel_idx_for(channel_index_list, x2.device)
-        partial = ops.channel_gather(x2, idx)              # [T, n] packed copy, ONE launch (smt.py:240-247)
+        # packed copy of the selected input channels, ONE launch (smt.py:240-247 does n strided slice copies); padded
+        # with zero columns so that the tcgen05 gradient kernel can read it through TMA (16-byte row pitch) - fp32 inputs
+        # take the fp32 block kernel, which wants whole 64-column blocks
+        pad = 64 if x2.dtype == torch.float32 else 8
+        partial = ops.channel_gather(x2, _channel_idx_for(channel_index_list, x2.device, pad))
+        ctx.n_channels = len(channel_index_list)
         ctx.save_for_backward(partial, weight)
         return torch.matmul(input, weight.t())            # smt.py:257
 
@@ -480,13 +486,43 @@ class linearChannel(torch.autograd.Function):
         partial, weight = ctx.saved_tensors
         grad_input = grad_weight = None
         if ctx.needs_input_grad[1]:
+            n = ctx.n_channels
             dy2 = grad_output.reshape(-1, grad_output.shape[-1])
-            # smt.py:283-284: sum over the batch of partial^T @ dy — here one plain TN GEMM over all tokens
-            # (library GEMM, fp32 accumulation, one rounding)
-            grad_weight = torch.matmul(partial.t().to(dy2.dtype), dy2)
+            if dy2.stride(-1) != 1 or (dy2.stride(0) * dy2.element_size()) % 16 != 0:
+                dy2 = dy2.contiguous()
+            if partial.dtype != dy2.dtype:
+                partial = partial.to(dy2.dtype)
+            out_f = dy2.shape[1]
+            # smt.py:283-284: sum over the batch of partial^T @ dy == ONE contraction over all tokens, on the same
+            # tcgen05 pipeline as the block gradients (fp32 accumulation, one rounding)
+            if n == 0:
+                grad_weight = torch.zeros(0, out_f, dtype=dy2.dtype, device=dy2.device)
+            elif dy2.dtype == torch.float32 or out_f % 64 != 0:
+                grad_weight = _channel_grad_by_blocks(partial, n, dy2)
+            else:
+                grad_weight = ops.channel_grad_gemm(partial, n, dy2)
         if ctx.needs_input_grad[0]:
             grad_input = torch.matmul(grad_output, weight)                                      # smt.py:286
         return grad_input, grad_weight, None, None
+
+
+def _channel_grad_by_blocks(partial, n, dy2):
+    """fp32 (parity configuration) / odd widths: the same contraction through the single-problem block-gradient entry
+    point - every 64 x 64 block of the [n64, out64] result - followed by an un-tiling copy."""
+    b = 64
+    T, out_f = dy2.shape
+    n64 = partial.shape[1]
+    if n64 % b:
+        partial = torch.nn.functional.pad(partial, (0, b - n64 % b))
+        n64 = partial.shape[1]
+    out64 = (out_f + b - 1) // b * b
+    if out64 != out_f:
+        dy2 = torch.nn.functional.pad(dy2, (0, out64 - out_f))
+    rows, cols = n64 // b, out64 // b
+    rc = ops.make_block_rc([(r, c) for r in range(rows) for c in range(cols)], dy2.device)
+    tiles = ops.block_grad_gemm(dy2.contiguous(), partial.contiguous(), rc, b, out_dtype=dy2.dtype)
+    full = tiles.view(rows, cols, b, b).permute(0, 2, 1, 3).reshape(n64, out64)
+    return full[:n, :out_f].contiguous()
 
 
 class LinearLayer_ChannelSparsity(nn.Module):

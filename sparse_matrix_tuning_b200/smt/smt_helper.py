@@ -214,6 +214,35 @@ def select_channel_based_on_activation(activation,
     return _select_from_device_scores(keys, scores, n, selection_strategy, lambda ki, lo: lo)
 
 
+def select_submatrix_based_on_activation(activation,
+                                         targeted_module_dims,
+                                         n=660,
+                                         selection_strategy="no_restriction",
+                                         calculate_strategy="mean_abs",
+                                         model="yahma/llama-13b-hf"):
+    """EXTENSION - no reference counterpart, **parity unpinned** (caveat iii).
+
+    The reference's activation path selects input CHANNELS and trains them through a channel layer that only works for
+    square weights; it has no activation-based BLOCK selection, although its headline
+    configuration "activation-based selection incl. MLP blocks" suggests one.  This helper defines it in the obvious
+    way so that the block-sparse training path can be driven by activation statistics: the score of block (r, c) of
+    W[out, in] is the sum of the channel scores (exactly those of `select_channel_based_on_activation`,
+    smt_helper.py:168-183) of the b input channels of block column c - the same for every block row r - and the top-n
+    blocks are picked by the same heap / tie rule as the gradient-based selection (smt_helper.py:102-146).  Returns the
+    `{(module, layer): [(row, col), ...]}` dict `convert_linear_layer_to_matrix_sparsity` takes."""
+    block = Block_dimension
+    keys, ch_scores = channel_scores_on_device(activation, calculate_strategy)
+    scores = []
+    for key, cs in zip(keys, ch_scores):
+        rows = int(targeted_module_dims[key[0]][0] / block)
+        cols = int(targeted_module_dims[key[0]][1] / block)
+        if cs.numel() != cols * block:
+            raise SMTLibraryError(f"activation of {key} has {cs.numel()} channels, expected {cols * block}")
+        per_col = cs.view(cols, block).sum(dim=1)            # 16-56 numbers per matrix: host-scale glue, not a kernel
+        scores.append(per_col.unsqueeze(0).expand(rows, cols).contiguous())
+    return select_submatrix_from_scores(keys, scores, n, selection_strategy)
+
+
 # ---- block budget (the driver-side arithmetic of fine_tune.py:217-241, as callable helpers) ---------------------------
 
 _TARGETED_MODULE_NAMES = ("gate_proj", "up_proj", "down_proj", "q_proj", "k_proj", "v_proj")    # fine_tune.py:217-220

@@ -810,3 +810,86 @@ def test_channel_modules_in_merged_export_and_resume(api):
     CK.load_smt_state(net, state)
     assert torch.equal(layer.selected_weight.detach(), state["selected_weight"]["layers.0"])
     assert torch.equal(layer.weight[:, idx].t().contiguous(), layer.selected_weight.detach())
+
+
+def test_smtadam_under_the_drivers_lr_scheduler(api):
+    """fine_tune.py:367-373: the SMT phase builds `get_scheduler("linear", optimizer, num_warmup_steps=smt_lr_warmup_steps,
+    num_training_steps=...)` over the new optimizer; group 0's lr starts from smt_lr (smt.py:517-518 overrides the
+    optimizer's lr).  SMTAdam must follow the schedule exactly like torch.optim.AdamW on fp32 copies of the same blocks."""
+    M, _H = api
+    from transformers import get_scheduler
+    from sparse_matrix_tuning_b200.optim import SMTAdam
+    torch.manual_seed(12)
+    w = torch.nn.Parameter(torch.randn(512, 512, device="cuda") * 0.05)            # fp32: masters == parameters
+    layer = M.LinearLayer_MatrixSparsity(w, index_list=[(1, 0), (0, 1)])
+    holder = torch.nn.Module()
+    holder.layer = layer
+    groups = M.get_optimizer_sparse_grouped_parameters(holder, 0.0, 3e-4)
+    opt = SMTAdam(groups, lr=9.65e-6, betas=(0.9, 0.95))                            # fine_tune.py:352-363
+    sched = get_scheduler(name="linear", optimizer=opt, num_warmup_steps=3, num_training_steps=10)
+    ref_p = torch.nn.Parameter(layer.selected_weight.detach().clone())
+    ref_opt = torch.optim.AdamW([{"params": [ref_p], "lr": 3e-4, "weight_decay": 0.0}], lr=9.65e-6, betas=(0.9, 0.95),
+                                eps=1e-8)
+    ref_sched = get_scheduler(name="linear", optimizer=ref_opt, num_warmup_steps=3, num_training_steps=10)
+    lrs = []
+    for step in range(8):
+        g = torch.Generator(device="cuda").manual_seed(step)
+        x = torch.randn(2, 32, 512, device="cuda", generator=g)
+        dy = torch.randn(2, 32, 512, device="cuda", generator=g)
+        opt.zero_grad()
+        layer(x).backward(dy)
+        ref_p.grad = layer.selected_weight.grad.detach().clone()
+        opt.step()
+        sched.step()
+        ref_opt.step()
+        ref_sched.step()
+        lrs.append(opt.param_groups[0]["lr"])
+        assert opt.param_groups[0]["lr"] == ref_opt.param_groups[0]["lr"]
+        assert (layer.selected_weight.detach() - ref_p.detach()).abs().max().item() <= 2e-6 * (step + 1)
+    assert lrs[0] == pytest.approx(3e-4 / 3) and lrs[2] == pytest.approx(3e-4) and lrs[-1] < lrs[3]   # warm-up, then decay
+    assert torch.equal(O.gather_blocks(w.detach().cpu(), layer.index_list, 256), layer.selected_weight.detach().cpu())
+
+
+@pytest.mark.parametrize("n,out_f,T,dtype", [(1, 1024, 300, torch.bfloat16), (5, 4096, 1000, torch.bfloat16),
+                                              (100, 1024, 2048, torch.float16), (130, 14336, 777, torch.bfloat16),
+                                              (64, 512, 64, torch.bfloat16)])
+def test_channel_grad_gemm_vs_fp32_matmul(api, n, out_f, T, dtype):
+    """The channel-sparsity weight gradient `partial_input^T @ grad_output` (smt.py:283-284) on the tcgen05 pipeline:
+    packed channels padded by TMA zero fill, tiles stored with the row pitch of the [n, out] result.  fp32 accumulation,
+    one rounding: within 2^-8 of the tensor max of the fp32 product (half an ulp of the largest element)."""
+    from sparse_matrix_tuning_b200 import ops
+    torch.manual_seed(n)
+    x = torch.randn(T, 2048, device="cuda").to(dtype)
+    dy = torch.randn(T, out_f, device="cuda").to(dtype)
+    idx_list = torch.randperm(2048)[:n].tolist()
+    idx = ops.make_channel_idx(idx_list, "cuda", pad_to=8)
+    partial = ops.channel_gather(x, idx)
+    assert partial.shape == (T, (n + 7) // 8 * 8)
+    assert torch.equal(partial[:, :n], x[:, idx_list]) and not partial[:, n:].any()
+    got = ops.channel_grad_gemm(partial, n, dy)
+    want = x[:, idx_list].float().t() @ dy.float()
+    assert got.shape == (n, out_f) and got.dtype == dtype
+    assert (got.float() - want).abs().max().item() <= 2 ** -8 * want.abs().max().item()
+    assert torch.equal(got, ops.channel_grad_gemm(partial, n, dy))            # deterministic
+
+
+def test_activation_based_block_selection_extension(api):
+    """Block scores from activations (extension, parity unpinned): block column score = sum of its channels' scores
+    (channel scores pinned by the reference goldens), same for every block row; top-n by the shared tie rule."""
+    M, H = api
+    torch.manual_seed(4)
+    b = 256
+    act = {("q_proj", 0): torch.rand(2, 16, 1024), ("k_proj", 0): torch.rand(2, 16, 1024), ("down_proj", 1): torch.rand(2, 16, 512)}
+    act[("k_proj", 0)][:, :, 256:512] += 5.0                                   # plant one hot block column
+    dims = {"q_proj": [1024, 1024], "k_proj": [512, 1024], "down_proj": [1024, 512]}
+    sel = H.select_submatrix_based_on_activation(act, dims, 3)
+    # the planted column outranks everything; with equal scores in a column the tie rule prefers the larger (i, j) tuple
+    assert sel[("k_proj", 0)][:2] == [(1, 1), (0, 1)]
+    want = {}
+    for key, a in act.items():
+        cs = O.channel_scores(a, "mean_abs")
+        per_col = cs.view(-1, b).sum(1)
+        rows = dims[key[0]][0] // b
+        want[key] = per_col.unsqueeze(0).expand(rows, -1).contiguous()
+    ref = O.select_from_scores(want, 3)
+    assert {k: v for k, v in sel.items()} == {k: v for k, v in ref.items()}

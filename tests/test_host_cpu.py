@@ -241,3 +241,28 @@ def test_reference_driver_import_lines_resolve_to_this_package():
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd="/tmp", timeout=300)
     assert out.returncode == 0, out.stderr
     assert os.path.join("sparse_matrix_tuning_b200", "smt", "smt.py") in out.stdout
+
+
+def test_block_budget_helpers_match_the_reference_golden():
+    """a-3: the PRODUCT helpers `smt_helper.targeted_module_dims / num_total_blocks / block_budget` restate the driver's
+    inline arithmetic (fine_tune.py:217-241) and must reproduce the numbers the reference-generated config-1 golden
+    holds: 596 blocks in total (embeddings and lm_head included), int(0.01 * 596) = 5, and the dims dict."""
+    from conftest import load_golden
+    from oracle import golden_inputs as GI
+    from sparse_matrix_tuning_b200.smt import smt_helper as H
+    gold = load_golden("config1_e2e.pt")
+    model, _batches = GI.make_config1()
+    assert H.num_total_blocks(model) == gold["total_blocks"] == 596
+    assert H.block_budget(model, GI.CONFIG1["attn_ratio"]) == gold["n_attn"] == 5
+    assert H.targeted_module_dims(model) == gold["dims"]
+    assert H.block_budget(model, 0.0084) == int(0.0084 * 596)            # truncation, not rounding (fine_tune.py:236)
+    assert H.block_budget(model, 0.01, block=128) == int(0.01 * 596 * 4)
+    # LLaMA-3-8B: the figures BASELINE.md quotes, from shapes alone (meta tensors, nothing allocated)
+    import torch
+    from transformers import LlamaConfig, LlamaForCausalLM
+    cfg = LlamaConfig(vocab_size=128256, hidden_size=4096, intermediate_size=14336, num_hidden_layers=32,
+                      num_attention_heads=32, num_key_value_heads=8, tie_word_embeddings=False)
+    with torch.device("meta"):
+        big = LlamaForCausalLM(cfg)
+    assert H.num_total_blocks(big) == 122528 and H.block_budget(big, 0.0071) == 869 and H.block_budget(big, 0.0086) == 1053
+    assert H.targeted_module_dims(big)["k_proj"] == [1024, 4096]
