@@ -201,6 +201,26 @@ SMT_API int smt_debug_set_gemm_trace(void* dev_buf, int max_ctas);
 SMT_API int smt_block_grad_gemm_plan(int n_blocks, int block, int64_t T, int in_dtype,
                              int* splits_host, int* ctas_host);
 
+/* ---- dense side of linearZ, fused over modules that share their input (q, k, v of a decoder layer) ------------- */
+
+/* forward:  y_j[T, N_j] = x[T, K] . W_j[N_j, K]^T  for j < n_seg (<= 3)   — linearZ.forward, smt.py:366, once instead of
+ *           once per module; x is read once, the N tiles of [W_0; W_1; W_2] are walked as one weight.
+ * dgrad:    dx[T, K]   = sum_j dy_j[T, N_j] . W_j[N_j, K]                 — linearZ.backward's grad_input, smt.py:406,
+ *           for all modules at once: the reduction runs through the n_seg (dy_j, W_j) pairs into one accumulator, so
+ *           the elementwise adds autograd inserts between three separate results disappear.
+ * Hand-written persistent tcgen05 kernel (cta_group::2, 256 x 256 tiles, TMA-fed, double-buffered TMEM accumulators),
+ * fp32 accumulation, one rounding to `dtype` (bf16 / f16 = the dtype of every operand and result).
+ * Constraints (smt_fused_linear_supported tells): K % 64 == 0; N_j % 64 == 0, and N_j % 256 == 0 for forward (an N tile
+ * must not straddle two modules); 16-byte aligned pointers and row pitches; any T (edge tiles are clipped).
+ * `*_host` arrays live in HOST memory (n_seg entries); all matrices are device pointers, row-major, `ld*` in elements. */
+SMT_API int smt_fused_linear_supported(int n_seg, const int* N_host, int K, int dtype, int dgrad);
+SMT_API int smt_fused_linear_forward(const void* x, int64_t ldx, int64_t T, int K, int n_seg,
+                                     const void* const* W_host, const int64_t* ldw_host, const int* N_host,
+                                     void* const* y_host, const int64_t* ldy_host, int dtype, void* stream);
+SMT_API int smt_fused_linear_dgrad(const void* const* dy_host, const int64_t* lddy_host, int64_t T, int K, int n_seg,
+                                   const void* const* W_host, const int64_t* ldw_host, const int* N_host,
+                                   void* dx, int64_t lddx, int dtype, void* stream);
+
 /* ---- compact optimizer ---------------------------------------------------------------- */
 
 /* out_sqnorm[0] = sum grad[i]^2 (fp32, deterministic two-stage tree). workspace: 4 KiB floats. */

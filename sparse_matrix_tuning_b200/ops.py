@@ -400,6 +400,74 @@ def block_grad_gemm_plan(n_blocks: int, block: int, T: int, dtype: torch.dtype) 
     return a.value, b.value
 
 
+# ---- dense side of linearZ, fused over modules that share their input ---------------------------------------------
+
+def fused_linear_supported(weights: Sequence[torch.Tensor], dgrad: bool = False) -> bool:
+    """True when `fused_linear_forward` / `fused_linear_dgrad` can take these weights (1-3 [N_j, K] matrices of one
+    16-bit dtype on one CUDA device with aligned storage); the caller keeps the per-module library GEMMs otherwise."""
+    if not 1 <= len(weights) <= 3:
+        return False
+    w0 = weights[0]
+    if not w0.is_cuda or w0.dtype not in (torch.bfloat16, torch.float16):
+        return False
+    for w in weights:
+        if w.dim() != 2 or w.dtype != w0.dtype or w.device != w0.device or w.shape[1] != w0.shape[1] or w.stride(1) != 1:
+            return False
+        if w.data_ptr() % 16 or (w.stride(0) * 2) % 16:
+            return False
+    ns = (C.c_int * len(weights))(*[int(w.shape[0]) for w in weights])
+    return bool(load().smt_fused_linear_supported(len(weights), ns, int(w0.shape[1]), dtype_id(w0.dtype), 1 if dgrad else 0))
+
+
+def _seg_arrays(tensors: Sequence[torch.Tensor]):
+    n = len(tensors)
+    ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in tensors])
+    lds = (C.c_int64 * n)(*[t.stride(0) for t in tensors])
+    return ptrs, lds
+
+
+def fused_linear_forward(x2d: torch.Tensor, weights: Sequence[torch.Tensor]) -> list:
+    """[x2d @ W_j^T for j] in ONE tcgen05 launch (smt.py:366 for every module that reads x).  x2d: [T, K]."""
+    require_cuda(x2d, *weights)
+    _req(x2d.dim() == 2 and x2d.stride(1) == 1 and x2d.dtype == weights[0].dtype and x2d.shape[1] == weights[0].shape[1],
+         "x2d.dim() == 2 and x2d.stride(1) == 1 and x2d.dtype == weights[0].dtype and x2d.shape[1] == K")
+    _req(x2d.data_ptr() % 16 == 0 and (x2d.stride(0) * 2) % 16 == 0, "16-byte aligned x")
+    T, K = x2d.shape
+    ys = [torch.empty(T, w.shape[0], dtype=x2d.dtype, device=x2d.device) for w in weights]
+    n = len(weights)
+    wp, wl = _seg_arrays(weights)
+    yp, yl = _seg_arrays(ys)
+    ns = (C.c_int * n)(*[int(w.shape[0]) for w in weights])
+    with _timed("fused_linear_forward", x2d.device, (T, K, sum(w.shape[0] for w in weights))):
+        check(load().smt_fused_linear_forward(ptr(x2d), x2d.stride(0) if T > 0 else K, T, K, n, wp, wl, ns, yp, yl,
+                                              dtype_id(x2d.dtype), _st(x2d)), "smt_fused_linear_forward")
+    if T > 0:
+        _count()
+    return ys
+
+
+def fused_linear_dgrad(dys: Sequence[torch.Tensor], weights: Sequence[torch.Tensor]) -> torch.Tensor:
+    """sum_j dy_j @ W_j in ONE tcgen05 launch (smt.py:406 for every module that reads x, plus autograd's adds)."""
+    require_cuda(*dys, *weights)
+    _req(len(dys) == len(weights) and len(dys) >= 1, "len(dys) == len(weights) >= 1")
+    T, K = dys[0].shape[0], weights[0].shape[1]
+    for dy, w in zip(dys, weights):
+        _req(dy.dim() == 2 and dy.stride(1) == 1 and dy.shape == (T, w.shape[0]) and dy.dtype == w.dtype,
+             "dy.dim() == 2 and dy.stride(1) == 1 and dy.shape == (T, N_j) and dy.dtype == w.dtype")
+        _req(dy.data_ptr() % 16 == 0 and (dy.stride(0) * 2) % 16 == 0, "16-byte aligned dy")
+    dx = torch.empty(T, K, dtype=dys[0].dtype, device=dys[0].device)
+    n = len(weights)
+    wp, wl = _seg_arrays(weights)
+    dp_, dl = _seg_arrays(dys)
+    ns = (C.c_int * n)(*[int(w.shape[0]) for w in weights])
+    with _timed("fused_linear_dgrad", dx.device, (T, K, sum(w.shape[0] for w in weights))):
+        check(load().smt_fused_linear_dgrad(dp_, dl, T, K, n, wp, wl, ns, ptr(dx), K, dtype_id(dx.dtype), _st(dx)),
+              "smt_fused_linear_dgrad")
+    if T > 0:
+        _count()
+    return dx
+
+
 # ---- optimizer ---------------------------------------------------------------------------------------------
 
 def grad_sqnorm(grad: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -201,35 +201,43 @@ class linearZ(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_output):
         x, weight = ctx.saved_tensors
-        b = ctx.block
         grad_input = grad_weight = None
         if ctx.needs_input_grad[1]:
-            n = len(ctx.index_list)
-            x2 = x.reshape(-1, x.shape[-1])
-            dy2 = grad_output.reshape(-1, grad_output.shape[-1])
-            if dy2.stride(-1) != 1 or (dy2.stride(0) * dy2.element_size()) % 16 != 0:
-                dy2 = dy2.contiguous()
-            if x2.stride(-1) != 1 or (x2.stride(0) * x2.element_size()) % 16 != 0:
-                x2 = x2.contiguous()
-            if x2.dtype != dy2.dtype:
-                x2 = x2.to(dy2.dtype)
-            rc = _block_rc_for(ctx.index_list, dy2.device)
-            sink = getattr(ctx.sw_ref, "_smt_sink", None)
-            if sink is not None:
-                # native mode: deliver straight into the flat (NCCL) gradient buffer, nothing returned.  The sink says
-                # whether this delivery accumulates or overwrites (first one after a lazy zero_grad).
-                accumulate = sink.begin_delivery(ctx.sw_ref)
-                if _grouped["enabled"] and dy2.dtype != torch.float32 and n > 0:
-                    _enqueue_block_grad(x2, dy2, ctx.index_list, sink, b, accumulate)   # grouped launch(es) per backward
-                else:
-                    ops.block_grad_gemm(x2, dy2, rc, b, out=sink.view, accumulate=accumulate)
-                    sink.sq_ok = False
-            else:
-                grad_weight = ops.block_grad_gemm(x2, dy2, rc, b, out_dtype=grad_output.dtype)  # smt.py:382-404
-                grad_weight = grad_weight.view(n * b, b)
+            x2 = _as_operand(x.reshape(-1, x.shape[-1]))
+            dy2 = _as_operand(grad_output.reshape(-1, grad_output.shape[-1]))
+            grad_weight = _block_weight_grad(ctx.sw_ref, ctx.index_list, x2, dy2, ctx.block, grad_output.dtype)
         if ctx.needs_input_grad[0]:
             grad_input = torch.matmul(grad_output, weight)                                      # smt.py:406
         return grad_input, grad_weight, None, None
+
+
+def _as_operand(t2):
+    """[T, features] view usable by TMA: unit column stride, 16-byte row pitch and base."""
+    if t2.stride(-1) != 1 or (t2.stride(0) * t2.element_size()) % 16 != 0 or t2.data_ptr() % 16 != 0:
+        t2 = t2.contiguous()
+    return t2
+
+
+def _block_weight_grad(sw_param, index_list, x2, dy2, b, out_dtype):
+    """The block gradients of one module (smt.py:382-404).  Native mode (the parameter owns a GradSink, i.e. it lives
+    in an SMTAdam arena): delivered straight into the flat gradient buffer - grouped with the other modules of the
+    backward pass when grouping is enabled - and None is returned; otherwise the [n*b, b] gradient is returned."""
+    n = len(index_list)
+    if x2.dtype != dy2.dtype:
+        x2 = x2.to(dy2.dtype)
+    sink = getattr(sw_param, "_smt_sink", None)
+    if sink is not None:
+        # the sink says whether this delivery accumulates or overwrites (first one after a lazy zero_grad)
+        accumulate = sink.begin_delivery(sw_param)
+        if _grouped["enabled"] and dy2.dtype != torch.float32 and n > 0:
+            _enqueue_block_grad(x2, dy2, index_list, sink, b, accumulate)   # grouped launch(es) per backward
+        else:
+            rc = _block_rc_for(index_list, dy2.device)
+            ops.block_grad_gemm(x2, dy2, rc, b, out=sink.view, accumulate=accumulate)
+            sink.sq_ok = False
+        return None
+    rc = _block_rc_for(index_list, dy2.device)
+    return ops.block_grad_gemm(x2, dy2, rc, b, out_dtype=out_dtype).view(n * b, b)                # smt.py:382-404
 
 
 class LinearLayer_MatrixSparsity(nn.Module):
@@ -305,6 +313,132 @@ class LinearLayer_MatrixSparsity(nn.Module):
         return self.fn(x, self.selected_weight, self.index_list, self.weight)   # smt.py:343
 
 
+# ---- fused q/k/v projections (the dense side of linearZ) --------------------------------
+#
+# q_proj, k_proj and v_proj of a decoder layer read the same hidden states.  The reference runs them as three
+# independent modules: three `x @ W^T` GEMMs in forward (smt.py:366), three `dy @ W` GEMMs in backward (smt.py:406) whose
+# results autograd adds with two elementwise kernels.  `fuse_qkv_projections(model)` ties the three modules of every
+# layer into a group: the first call (q_proj) runs ONE hand-written tcgen05 GEMM over [Wq; Wk; Wv] and hands k_proj /
+# v_proj their slices when they are called with the same tensor; backward runs ONE GEMM over K = 4096 + 1024 + 1024
+# for the input gradient and feeds the block-gradient path of each sparse member.  Module names, parameters and
+# state dicts are untouched (the override is an instance attribute); members may be LinearLayer_MatrixSparsity or frozen,
+# bias-free nn.Linear.  Anything the kernel does not support falls back to the members' own forward.
+
+class fusedLinearZ(torch.autograd.Function):
+    """forward(ctx, input, group, *selected_weights of the sparse members) -> one output per member."""
+
+    @staticmethod
+    def forward(ctx, input, group, *selected_weights):
+        weights = [m.weight for m in group.members]
+        x2 = _as_operand(input.reshape(-1, input.shape[-1]))
+        ys = ops.fused_linear_forward(x2, [w.data for w in weights])
+        ctx.group = group
+        ctx.block = Block_dimension
+        ctx.save_for_backward(input, *weights)
+        lead = input.shape[:-1]
+        return tuple(y.view(*lead, y.shape[-1]) for y in ys)
+
+    @staticmethod
+    def backward(ctx, *grad_outputs):
+        x, *weights = ctx.saved_tensors
+        members = ctx.group.members
+        dys = [_as_operand(g.reshape(-1, g.shape[-1])) for g in grad_outputs]
+        grad_input = None
+        if ctx.needs_input_grad[0]:
+            grad_input = ops.fused_linear_dgrad(dys, [w.data for w in weights]).view(x.shape)   # smt.py:406, all members
+        grads, k = [], 0
+        x2 = None
+        for m, dy2 in zip(members, dys):
+            if not isinstance(m, LinearLayer_MatrixSparsity):
+                continue
+            g = None
+            if ctx.needs_input_grad[2 + k]:
+                if x2 is None:
+                    x2 = _as_operand(x.reshape(-1, x.shape[-1]))
+                g = _block_weight_grad(m.selected_weight, m.index_list, x2, dy2, ctx.block, dy2.dtype)
+            grads.append(g)
+            k += 1
+        return (grad_input, None, *grads)
+
+
+class _SharedInputGroup:
+    """q_proj / k_proj / v_proj of one attention layer, in call order."""
+
+    def __init__(self, members):
+        self.members = list(members)
+        self._cache = None           # (input tensor, [outputs still to be handed out])
+        self._ok_key = None
+
+    def _supported(self, x) -> bool:
+        ws = [m.weight for m in self.members]
+        if not (x.is_cuda and x.dim() >= 2 and x.dtype == ws[0].dtype and x.shape[-1] == ws[0].shape[1]):
+            return False
+        key = tuple((w.data_ptr(), w.stride(0), w.dtype) for w in ws)
+        if self._ok_key != key:
+            ok = ops.fused_linear_supported([w.data for w in ws], dgrad=False) and \
+                ops.fused_linear_supported([w.data for w in ws], dgrad=True)
+            self._ok_key = key if ok else None
+            if not ok:
+                return False
+        return True
+
+    def call(self, role: int, module, x):
+        c = self._cache
+        if role != 0 and c is not None and c[0] is x and c[1][role] is not None:
+            y, c[1][role] = c[1][role], None
+            if all(o is None for o in c[1]):
+                self._cache = None
+            return y
+        if role == 0 and self._supported(x):
+            sparse = [m for m in self.members if isinstance(m, LinearLayer_MatrixSparsity)]
+            for m in sparse:
+                m.sync_weight()                                        # smt.py:332-341, unless SMTAdam vouches
+            outs = list(fusedLinearZ.apply(x, self, *[m.selected_weight for m in sparse]))
+            y, outs[0] = outs[0], None
+            self._cache = (x, outs)
+            return y
+        return type(module).forward(module, x)                         # different input / unsupported: the plain path
+
+
+def _fusable_member(m) -> bool:
+    if isinstance(m, LinearLayer_MatrixSparsity):
+        return True
+    return isinstance(m, nn.Linear) and m.bias is None and not m.weight.requires_grad
+
+
+def fuse_qkv_projections(model) -> int:
+    """Ties q_proj / k_proj / v_proj of every attention module into one fused dense GEMM per direction (see above).
+    Returns the number of layers fused.  Call after `convert_linear_layer_to_matrix_sparsity`; undone by
+    `unfuse_qkv_projections` (and automatically by `convert_matrix_sparsity_to_linear_layer`)."""
+    fused = 0
+    for parent in model.modules():
+        trio = [getattr(parent, n, None) for n in ("q_proj", "k_proj", "v_proj")]
+        if any(t is None for t in trio) or not all(_fusable_member(t) for t in trio):
+            continue
+        if any(getattr(t, "_smt_shared_group", None) is not None for t in trio):
+            continue
+        ws = [t.weight for t in trio]
+        if not all(w.is_cuda for w in ws) or not ops.fused_linear_supported([w.data for w in ws], dgrad=False) \
+                or not ops.fused_linear_supported([w.data for w in ws], dgrad=True):
+            continue
+        group = _SharedInputGroup(trio)
+        for role, mod in enumerate(trio):
+            mod._smt_shared_group = group
+            mod.forward = (lambda x, _g=group, _r=role, _m=mod: _g.call(_r, _m, x))
+        fused += 1
+    return fused
+
+
+def unfuse_qkv_projections(model) -> int:
+    n = 0
+    for mod in model.modules():
+        if getattr(mod, "_smt_shared_group", None) is not None:
+            mod.__dict__.pop("forward", None)
+            mod.__dict__.pop("_smt_shared_group", None)
+            n += 1
+    return n // 3
+
+
 # ---- model surgery ---------------------------------------------------------------------------------------
 
 def _selection_key_and_table(name: str, mixture: bool, selected_submatrix, selected_submatrix_attention):
@@ -347,6 +481,7 @@ def convert_linear_layer_to_matrix_sparsity(model,
 def convert_matrix_sparsity_to_linear_layer(model, part_module_name=['.layers']):
     """Reference: smt.py:416-457: write the trained blocks back and restore plain nn.Linear modules that
     share the (now merged) weight Parameter."""
+    unfuse_qkv_projections(model)
     names = [name for name, module in model.named_modules()
              if isinstance(module, LinearLayer_MatrixSparsity) and any(part in name for part in part_module_name)]
     for name in names:

@@ -893,3 +893,82 @@ def test_activation_based_block_selection_extension(api):
         want[key] = per_col.unsqueeze(0).expand(rows, -1).contiguous()
     ref = O.select_from_scores(want, 3)
     assert {k: v for k, v in sel.items()} == {k: v for k, v in ref.items()}
+
+
+@pytest.mark.parametrize("ckpt,grouped", [(False, False), (True, True)])
+def test_fused_qkv_projections_match_the_unfused_model(api, ckpt, grouped):
+    """f-2: `fuse_qkv_projections` must not change what the model computes: same loss, same compact gradients, same
+    parameters after a step - with sparse and frozen members mixed, under checkpointing and grouped block gradients."""
+    M, _H = api
+    from transformers import LlamaConfig, LlamaForCausalLM
+    from sparse_matrix_tuning_b200 import ops
+    from sparse_matrix_tuning_b200.optim import SMTAdam
+
+    def run(fuse):
+        torch.manual_seed(0)
+        cfg = LlamaConfig(vocab_size=512, hidden_size=512, intermediate_size=1024, num_hidden_layers=3,
+                          num_attention_heads=8, num_key_value_heads=4, max_position_embeddings=128)
+        model = LlamaForCausalLM(cfg).cuda().bfloat16()
+        sel = {("q_proj", 0): [(0, 1), (1, 0)], ("k_proj", 0): [(0, 0)], ("v_proj", 0): [(0, 1)],
+               ("v_proj", 1): [(0, 0)], ("q_proj", 2): [(1, 1), (0, 0), (0, 1)]}      # layer 1: only v is sparse
+        M.freeze_unselected_matrix_layer(model, {}, sel)
+        M.convert_linear_layer_to_matrix_sparsity(model, {}, sel)
+        if ckpt:
+            model.gradient_checkpointing_enable(gradient_checkpointing_kwargs={"use_reentrant": False})
+            model.enable_input_require_grads()
+        model.train()
+        n_fused = M.fuse_qkv_projections(model) if fuse else 0
+        opt = SMTAdam(M.get_optimizer_sparse_grouped_parameters(model, 0.0, 1e-3), betas=(0.9, 0.95), max_grad_norm=1.0)
+        M.set_grouped_backward(grouped)
+        try:
+            ids = torch.randint(0, 512, (2, 96), generator=torch.Generator().manual_seed(1)).cuda()
+            losses = []
+            for _ in range(2):
+                opt.zero_grad()
+                n0 = ops.LAUNCHES["total"]
+                loss = model(input_ids=ids, labels=ids, use_cache=False).loss
+                loss.backward()
+                launches = ops.LAUNCHES["total"] - n0
+                grads = opt.flat_grads()[0].float().clone()
+                opt.step()
+                losses.append(loss.item())
+            params = torch.cat([p.detach().reshape(-1).float() for g in opt.param_groups for p in g["params"]])
+            names = sorted(k for k in model.state_dict().keys())
+            return losses, grads, params, n_fused, launches, names
+        finally:
+            M.set_grouped_backward(False)
+            M.unfuse_qkv_projections(model)
+
+    l0, g0, p0, _, _, names0 = run(False)
+    l1, g1, p1, n_fused, launches, names1 = run(True)
+    assert n_fused == 3 and names0 == names1                        # every layer fused; state dict keys untouched
+    assert launches >= 3 * (2 if ckpt else 1) + 3                   # fused forward (x2 with recomputation) + fused dgrad
+    assert abs(l1[0] - l0[0]) <= 2e-2 and abs(l1[1] - l0[1]) <= 2e-2   # bf16 logits: one rounding vs the library's
+    assert (g1 - g0).abs().max().item() <= 0.05 * g0.abs().max().item()
+    assert (p1 - p0).abs().max().item() <= 2.1e-3 * 2               # two Adam steps of lr 1e-3
+
+
+def test_fused_qkv_falls_back_when_called_out_of_pattern(api):
+    """k_proj called with a different tensor, or alone, must give its own x @ Wk^T (no stale slice of a fused call)."""
+    M, _H = api
+    from transformers import LlamaConfig, LlamaForCausalLM
+    torch.manual_seed(3)
+    cfg = LlamaConfig(vocab_size=256, hidden_size=512, intermediate_size=1024, num_hidden_layers=1,
+                      num_attention_heads=8, num_key_value_heads=4, max_position_embeddings=64)
+    model = LlamaForCausalLM(cfg).cuda().bfloat16()
+    M.freeze_unselected_matrix_layer(model, {}, {})
+    assert M.fuse_qkv_projections(model) == 1
+    attn = model.model.layers[0].self_attn
+    x = torch.randn(2, 16, 512, device="cuda").bfloat16()
+    x_other = torch.randn(2, 16, 512, device="cuda").bfloat16()
+    with torch.no_grad():
+        q = attn.q_proj(x)                                   # fused call: k and v slices are cached for `x`
+        k_other = attn.k_proj(x_other)                       # different tensor: plain path
+        k = attn.k_proj(x)                                   # the cached slice
+        v_alone = attn.v_proj(x_other)
+    ref = lambda t, w: (t.float() @ w.float().t())
+    tol = 2 ** -7
+    for got, want in ((q, ref(x, attn.q_proj.weight)), (k, ref(x, attn.k_proj.weight)),
+                      (k_other, ref(x_other, attn.k_proj.weight)), (v_alone, ref(x_other, attn.v_proj.weight))):
+        assert (got.float() - want).abs().max().item() <= tol * want.abs().max().item()
+    assert M.unfuse_qkv_projections(model) == 1 and "forward" not in attn.q_proj.__dict__

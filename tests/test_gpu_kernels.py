@@ -569,3 +569,65 @@ def test_grouped_gemm_2sm_token_count_edges(ops):
             got = out[i * len(idx) * b * b:(i + 1) * len(idx) * b * b].view(len(idx), b, b)
             want = torch.stack([ref[r * b:(r + 1) * b, c * b:(c + 1) * b] for r, c in idx])
             assert (got - want).abs().max().item() <= 2e-5 * max(want.abs().max().item(), 1e-3), T
+
+
+# ---- fused dense projections (dense side of linearZ: smt.py:366, 406) ------------------------------------------------
+
+@pytest.mark.parametrize("T,K,Ns,dtype", [
+    (1000, 512, [512, 256, 256], torch.bfloat16),          # ragged T, GQA-shaped q/k/v
+    (256, 1024, [256], torch.bfloat16),                    # one module, one tile
+    (2309, 1536, [1024, 256], torch.float16),              # two modules, f16, ragged T
+    (8192, 4096, [4096, 1024, 1024], torch.bfloat16),      # LLaMA-3-8B q/k/v at the bench's token count
+])
+def test_fused_linear_forward_vs_fp32(ops, T, K, Ns, dtype):
+    """ONE tcgen05 launch for every module that reads x: each y_j must equal x @ W_j^T (fp32 accumulation, one rounding)
+    - within half an ulp of the output type at the tensor's largest element plus the fp32 accumulation error."""
+    torch.manual_seed(T + K)
+    x = torch.randn(T, K, device="cuda").to(dtype)
+    ws = [(torch.randn(n, K, device="cuda") * 0.05).to(dtype) for n in Ns]
+    assert ops.fused_linear_supported(ws)
+    ys = ops.fused_linear_forward(x, ws)
+    eps = 2 ** -8 if dtype == torch.bfloat16 else 2 ** -11
+    for y, w in zip(ys, ws):
+        ref = x.float() @ w.float().t()
+        assert y.shape == ref.shape and y.dtype == dtype
+        assert (y.float() - ref).abs().max().item() <= (eps + 1e-4) * ref.abs().max().item()
+        lib = torch.matmul(x, w.t()).float()                                   # the library GEMM it replaces
+        assert (y.float() - ref).abs().max().item() <= 1.5 * (lib - ref).abs().max().item() + 1e-6
+    ys2 = ops.fused_linear_forward(x, ws)
+    assert all(torch.equal(a, b) for a, b in zip(ys, ys2))                    # deterministic
+
+
+@pytest.mark.parametrize("T,K,Ns,dtype", [
+    (1000, 512, [512, 256, 256], torch.bfloat16),
+    (300, 192, [320, 64], torch.bfloat16),                 # dx narrower than one N tile, reduction lengths not x 256
+    (2309, 1536, [1024, 256], torch.float16),
+    (8192, 4096, [4096, 1024, 1024], torch.bfloat16),
+])
+def test_fused_linear_dgrad_vs_fp32(ops, T, K, Ns, dtype):
+    """dx = sum_j dy_j @ W_j in ONE launch: the reduction runs through all (dy_j, W_j) pairs into one fp32 accumulator
+    (the reference adds three separately rounded bf16 results)."""
+    torch.manual_seed(T + K + 1)
+    ws = [(torch.randn(n, K, device="cuda") * 0.05).to(dtype) for n in Ns]
+    dys = [torch.randn(T, n, device="cuda").to(dtype) for n in Ns]
+    assert ops.fused_linear_supported(ws, dgrad=True)
+    dx = ops.fused_linear_dgrad(dys, ws)
+    ref = sum(dy.float() @ w.float() for dy, w in zip(dys, ws))
+    eps = 2 ** -8 if dtype == torch.bfloat16 else 2 ** -11
+    assert dx.shape == (T, K) and dx.dtype == dtype
+    err = (dx.float() - ref).abs().max().item()
+    assert err <= (eps + 1e-4) * ref.abs().max().item()
+    lib = sum(torch.matmul(dy, w) for dy, w in zip(dys, ws)).float()           # three library GEMMs + two bf16 adds
+    assert err <= 1.05 * (lib - ref).abs().max().item() + 1e-6                 # one rounding instead of five
+    assert torch.equal(dx, ops.fused_linear_dgrad(dys, ws))
+
+
+def test_fused_linear_rejects_unsupported_shapes(ops):
+    w_ok = torch.zeros(256, 512, device="cuda", dtype=torch.bfloat16)
+    assert ops.fused_linear_supported([w_ok])
+    assert not ops.fused_linear_supported([torch.zeros(128, 512, device="cuda", dtype=torch.bfloat16)])       # N % 256
+    assert ops.fused_linear_supported([torch.zeros(128, 512, device="cuda", dtype=torch.bfloat16)], dgrad=True)
+    assert not ops.fused_linear_supported([torch.zeros(256, 520, device="cuda", dtype=torch.bfloat16)])       # K % 64
+    assert not ops.fused_linear_supported([w_ok.float()])                                                      # fp32
+    assert not ops.fused_linear_supported([w_ok] * 4)
+    assert not ops.fused_linear_supported([w_ok, torch.zeros(256, 1024, device="cuda", dtype=torch.bfloat16)])
