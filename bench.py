@@ -62,6 +62,8 @@ def parse_args():
     ap.add_argument("--no-extra", action="store_true", help="skip the extra records (no-checkpointing, config 5, "
                                                             "config-2 points, score kernels, eager reference)")
     ap.add_argument("--no-group", action="store_true", help="launch the block-gradient GEMM per module instead of grouped")
+    ap.add_argument("--no-fuse-qkv", action="store_true", help="keep one library GEMM per q/k/v module instead of the fused "
+                                                               "tcgen05 projection / input-gradient kernels")
     ap.add_argument("--no-overlap", action="store_true", help="N>1: one blocking all-reduce after backward (round-1 behaviour)")
     ap.add_argument("--chunk-blocks", type=int, default=440, help="grouped GEMM flush granularity during backward (N>1)")
     ap.add_argument("--capture-steps", type=int, default=4, help="gradient-capture passes of the warm-up phase")
@@ -321,6 +323,46 @@ def config2_points(device, peaks):
     return pts
 
 
+def fused_qkv_ab(device, T, peaks):
+    """f-2, driver-visible A/B on this box: the fused tcgen05 q/k/v projection and the fused input gradient against the
+    library GEMMs they replace (three `torch.matmul` per direction + the two adds autograd inserts between the three
+    input gradients), LLaMA-3-8B q/k/v shapes at this run's token count.  CUDA events, 256 MB memset between
+    iterations."""
+    import torch
+    from sparse_matrix_tuning_b200 import ops
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
+    K, Ns = 4096, [4096, 1024, 1024]
+    x = torch.randn(T, K, device=device).bfloat16()
+    ws = [(torch.randn(n, K, device=device) * 0.02).bfloat16() for n in Ns]
+    dys = [torch.randn(T, n, device=device).bfloat16() for n in Ns]
+    flops = 2.0 * T * K * sum(Ns)
+    peak = peaks.get("bf16_tflops", 1599.5)
+
+    def lib_dgrad():
+        acc = torch.matmul(dys[0], ws[0])
+        for dy, w in zip(dys[1:], ws[1:]):
+            acc = acc + torch.matmul(dy, w)
+        return acc
+
+    out = {"shape": f"x[{T}, {K}] x [Wq; Wk; Wv]^T -> {'+'.join(map(str, Ns))} columns; dx over K = {sum(Ns)}",
+           "kernel": "fused_dense_umma_2sm_kernel (persistent, cta_group::2, 256x256 tiles, 6 stages, 2 TMEM accumulators)"}
+    for name, lib_fn, fused_fn in (("forward", lambda: [torch.matmul(x, w.t()) for w in ws],
+                                    lambda: ops.fused_linear_forward(x, ws)),
+                                   ("dgrad", lib_dgrad, lambda: ops.fused_linear_dgrad(dys, ws))):
+        t_lib = _median_ms(lib_fn, iters=9, warmup=3, flush=flush)
+        t_fus = _median_ms(fused_fn, iters=9, warmup=3, flush=flush)
+        out[name] = {"library_us": t_lib * 1e3, "library_tflops": flops / (t_lib * 1e-3) / 1e12,
+                     "fused_us": t_fus * 1e3, "fused_tflops": flops / (t_fus * 1e-3) / 1e12,
+                     "speedup": t_lib / t_fus, "bound": "tensor", "frac_of_bf16_burst": flops / (t_fus * 1e-3) / 1e12 / peak}
+    lib_total = 2 * out["forward"]["library_us"] + out["dgrad"]["library_us"]
+    fus_total = 2 * out["forward"]["fused_us"] + out["dgrad"]["fused_us"]
+    out["per_layer_step_us"] = {"library": lib_total, "fused": fus_total, "speedup": lib_total / fus_total,
+                                "note": "forward x 2 (gradient checkpointing recomputes it) + input gradient"}
+    del flush
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -440,10 +482,11 @@ def run_ours(args):
     del acc, acc_mlp
 
     # ---- extra, before the model is converted: score-kernel rooflines and config-2 points (rank 0 only) -------------
-    score_roof, cfg2 = None, None
+    score_roof, cfg2, qkv_ab = None, None, None
     if not args.no_extra and rank == 0:
         score_roof = score_kernel_rooflines(device, hbm_peak)
         cfg2 = config2_points(device, peaks)
+        qkv_ab = fused_qkv_ab(device, T, peaks)
     barrier()
 
     def convert(s_attn, s_mlp):
@@ -453,6 +496,7 @@ def run_ours(args):
         return SMTAdam(groups, lr=1e-4, betas=(0.9, 0.95), max_grad_norm=1.0)
 
     opt = convert(sel_attn, sel_mlp)
+    n_fused_layers = 0 if args.no_fuse_qkv else M.fuse_qkv_projections(model)
     sel = {**sel_attn, **sel_mlp}
     n_blocks = sum(len(v) for v in sel.values())
     trainable = opt.trainable_elements()
@@ -590,6 +634,8 @@ def run_ours(args):
     # ---- timed region 1: inputs resident in HBM ------------------------------------------------------------------
     ops.enable_timing("block_grad_gemm")
     ops.enable_timing("compact_adam")
+    ops.enable_timing("fused_linear_forward")
+    ops.enable_timing("fused_linear_dgrad")
     if exchange is not None:
         exchange.profile = True
     launches0 = ops.LAUNCHES["total"]
@@ -609,8 +655,10 @@ def run_ours(args):
     host_flush_ms = (ops.HOST_TIME["flush_s"] - host0["flush_s"]) * 1e3 / max(args.steps, 1)
     gemm_t = ops.collect_timing("block_grad_gemm")
     adam_t = ops.collect_timing("compact_adam")
-    ops.enable_timing("block_grad_gemm", False)
-    ops.enable_timing("compact_adam", False)
+    fwd_t = ops.collect_timing("fused_linear_forward")
+    dgr_t = ops.collect_timing("fused_linear_dgrad")
+    for name in ("block_grad_gemm", "compact_adam", "fused_linear_forward", "fused_linear_dgrad"):
+        ops.enable_timing(name, False)
     grouped_shape = dict(ops.LAST_GROUP)
     sq_source = getattr(opt, "sqnorm_source", None)
     phases = [[ev[k].elapsed_time(ev[k + 1]) for k in range(4)] for ev in phase_events]
@@ -652,14 +700,30 @@ def run_ours(args):
         barrier()
         ms_nockpt = e4.elapsed_time(e5)
         model.gradient_checkpointing_enable(gradient_checkpointing_kwargs={"use_reentrant": False})
+    # ---- extra: the same step with one library GEMM per q/k/v module (A/B of the fused dense kernels in the real step) ----
+    ms_unfused = None
+    if n_fused_layers and not args.no_extra:
+        M.unfuse_qkv_projections(model)
+        for i in range(2):
+            step(dev_ids[i])
+        barrier()
+        e6, e7 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e6.record()
+        for i in range(args.steps):
+            step(dev_ids[args.warmup + i])
+        e7.record()
+        barrier()
+        ms_unfused = e6.elapsed_time(e7)
+        M.fuse_qkv_projections(model)
     # ---- cross-rank reductions of the timings ------------------------------------------------------------------------
     breakdown = {"phases": ["forward", "backward (incl. grouped block-grad GEMM chunks)", "exchange wait", "adam + zero_grad"],
                  "mean_ms_this_rank": phase_mean, "host_flush_ms_per_step": host_flush_ms}
     if world > 1:
-        t = torch.tensor([ms_total, ms_e2e, ms_nockpt or 0.0], device=device, dtype=torch.float64)
+        t = torch.tensor([ms_total, ms_e2e, ms_nockpt or 0.0, ms_unfused or 0.0], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, ms_e2e, ms_nockpt = t.tolist()
+        ms_total, ms_e2e, ms_nockpt, ms_unfused = t.tolist()
         ms_nockpt = ms_nockpt or None
+        ms_unfused = ms_unfused or None
         mine = torch.tensor(phase_mean + [sum(phase_mean)], device=device, dtype=torch.float64)
         allp = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(allp, mine)
@@ -690,6 +754,8 @@ def run_ours(args):
             s5a, s5m = select(a5, m5, k5, k5)
             del a5, m5
             opt5 = convert(s5a, s5m)
+            if not args.no_fuse_qkv:
+                M.fuse_qkv_projections(model)
             M.set_grouped_backward(not args.no_group, chunk_blocks=args.chunk_blocks if overlap else 0)
             ex5 = dp.OverlappedGradExchange(opt5) if overlap else None
 
@@ -786,6 +852,8 @@ def run_ours(args):
         also.update(score_roof)
     if cfg2:
         also["config2"] = cfg2
+    if qkv_ab:
+        also["fused_qkv"] = qkv_ab
     roofline = {"kernel": gemm_kernel, "bound": "tensor", "achieved": achieved,
                 "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "traffic": traffic,
                 "traffic_note": traffic_note,
@@ -795,6 +863,15 @@ def run_ours(args):
                 "flops_per_launch": gemm_flops / max(n_gemm, 1), "share_of_step": gemm_ms / ms_total,
                 "also": also}
     smt_ms_per_step = (gemm_ms + sum(ms for ms, _ in adam_t)) / max(args.steps, 1)
+    dense_ms = sum(ms for ms, _ in fwd_t) + sum(ms for ms, _ in dgr_t)
+    dense_flops = sum(2.0 * t[0] * t[1] * t[2] for _ms, t in fwd_t) + sum(2.0 * t[0] * t[1] * t[2] for _ms, t in dgr_t)
+    if dense_ms > 0:
+        also.setdefault("fused_qkv", {})["in_step"] = {
+            "launches_per_step": (len(fwd_t) + len(dgr_t)) / max(args.steps, 1),
+            "ms_per_step": dense_ms / max(args.steps, 1),
+            "tflops": dense_flops / (dense_ms * 1e-3) / 1e12,
+            "frac_of_sustained_peak": dense_flops / (dense_ms * 1e-3) / 1e12 / peak_tf,
+            "share_of_step": dense_ms / ms_total}
     line = {"metric": METRIC, "value": value, "unit": "tokens/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "per_gpu_value": value / world,
@@ -805,6 +882,7 @@ def run_ours(args):
                        "selected_blocks": n_blocks, "block": BLOCK, "trainable_elements": trainable,
                        "modules_with_blocks": len(sel), "grouped_block_grad_launch": not args.no_group,
                        "grouped_launch_shape": grouped_shape,
+                       "fused_qkv_layers": n_fused_layers,
                        "total_blocks_budget_base": total_blocks, "gradient_checkpointing": not args.no_ckpt,
                        "parallelism": f"dp{world}", "tokens_per_step_per_gpu": T,
                        "gradient_exchange": ("none (1 GPU)" if world == 1 else
@@ -814,6 +892,7 @@ def run_ours(args):
                        "l2": "inputs larger than L2 (16 GB of weights streamed per step); no explicit flush",
                        "loss_last": last,
                        "tokens_per_s_without_checkpointing": (tokens / (ms_nockpt / 1e3)) if ms_nockpt else None,
+                       "ms_per_step_with_library_qkv_gemms": (ms_unfused / args.steps) if ms_unfused else None,
                        # SMT-layer-only view: the step is dominated by the HF model's dense GEMMs and elementwise kernels
                        # (out of scope); this is what the in-scope kernels alone cost per step
                        "smt_kernels_ms_per_step": smt_ms_per_step,

@@ -12,7 +12,7 @@ import threading
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_C", "libsmt_b200.so")
+LIB_PATH = os.environ.get("SMT_B200_LIB") or os.path.join(_HERE, "_C", "libsmt_b200.so")   # (override: kernel experiments)
 
 F32, BF16, F16 = 0, 1, 2
 MEAN_ABS, ABS_MEAN, L1, L2 = 0, 1, 2, 3

@@ -18,6 +18,7 @@
 // -> 128-byte row stores).  A is always K-major; B is K-major in forward (W[n, k], k contiguous) and MN-major in dgrad
 // (W[k, n], n contiguous): same TMA boxes / UMMA descriptors as the block-gradient kernel for the MN-major side.
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -326,6 +327,13 @@ int encode_dense_map(CUtensorMap* map, const void* base, int64_t cols, int64_t r
 
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// M tiles per raster group (SMT_DENSE_GROUP_M overrides the default for experiments)
+int dense_group_m() {
+  const char* v = getenv("SMT_DENSE_GROUP_M");
+  const int g = (v && *v) ? atoi(v) : 16;
+  return g > 0 ? g : 16;
+}
+
 template <bool DGRAD>
 int launch_dense(const DenseMaps& maps, const DenseParams& p, cudaStream_t st) {
   auto kern = fused_dense_umma_2sm_kernel<DGRAD>;
@@ -417,7 +425,7 @@ extern "C" SMT_API int smt_fused_linear_forward(const void* x, int64_t ldx, int6
   p.seg_tile0[n_seg] = tiles;
   p.n_tiles = tiles;
   p.m_tiles = (int)((T + kDenseTileM - 1) / kDenseTileM);
-  p.group_m = 8;
+  p.group_m = dense_group_m();
   if (int rc = launch_dense<false>(maps, p, (cudaStream_t)stream)) return rc;
   set_launch_count(1);
   return SMT_OK;
@@ -448,7 +456,7 @@ extern "C" SMT_API int smt_fused_linear_dgrad(const void* const* dy_host, const 
   p.ld_out[0] = lddx;
   p.n_tiles = (K + kDenseTileN - 1) / kDenseTileN;
   p.m_tiles = (int)((T + kDenseTileM - 1) / kDenseTileM);
-  p.group_m = 8;
+  p.group_m = dense_group_m();
   if (int rc = launch_dense<true>(maps, p, (cudaStream_t)stream)) return rc;
   set_launch_count(1);
   return SMT_OK;
