@@ -309,11 +309,12 @@ def config2_points(device, peaks):
         dy = torch.randn(T, fout, device=device).bfloat16()
         rc = ops.make_block_rc(idx, device)
         out = torch.empty(n * b, b, dtype=torch.bfloat16, device=device)
-        ms = _median_ms(lambda: ops.block_grad_gemm(x, dy, rc, b, out=out), iters=7, flush=flush)
+        ms = _median_ms(lambda: ops.block_grad_gemm(x, dy, rc, b, out=out, index_list=idx), iters=7, flush=flush)
         flops = 2.0 * b * b * T * n
         min_bytes = 2.0 * T * b * (len({r for r, _ in idx}) + len({c for _, c in idx})) + 2.0 * n * b * b
         bound_s = max(flops / (peak_tf * 1e12), min_bytes / (hbm * 1e9))
         pts.append({"weight": label, "block": b, "sparsity": frac_sel, "pattern": pattern, "T": T, "n_blocks": n,
+                    "kernel": ops.LAST_SINGLE.get("kernel"),
                     "us": ms * 1e3, "tflops": flops / (ms * 1e-3) / 1e12,
                     "bound": "tensor" if flops / (peak_tf * 1e12) >= min_bytes / (hbm * 1e9) else "hbm",
                     "frac_of_roofline": bound_s / (ms * 1e-3), "frac_of_bf16_burst": flops / (ms * 1e-3) / 1e12 / peak_tf})

@@ -35,6 +35,12 @@ class GemmItem(C.Structure):
 ITEM_OVERWRITE = 1   # SMT_ITEM_OVERWRITE
 
 
+class GemmRun(C.Structure):
+    """Mirror of `smt_gemm_run`."""
+    _fields_ = [("row", C.c_int32), ("half", C.c_int32), ("ncols", C.c_int32), ("cols", C.c_int32 * 4),
+                ("out_blk", C.c_int32 * 4), ("pad_", C.c_int32)]
+
+
 class SMTLibraryError(RuntimeError):
     pass
 
@@ -61,6 +67,10 @@ _SIGNATURES = {
     "smt_block_grad_gemm_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int64, C.c_int]),
     "smt_block_grad_gemm": (C.c_int, [_P, C.c_int64, C.c_int, _P, C.c_int64, C.c_int, C.c_int64, C.c_int,
                                       _P, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, C.c_size_t, _P]),
+    "smt_block_grad_gemm_run_width": (C.c_int, [C.c_int]),
+    "smt_block_grad_gemm_runs_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int64]),
+    "smt_block_grad_gemm_runs": (C.c_int, [_P, C.c_int64, C.c_int, _P, C.c_int64, C.c_int, C.c_int64, C.c_int,
+                                           _P, C.c_int, C.c_int, _P, C.c_int, C.c_int, _P, C.c_size_t, _P]),
     "smt_debug_set_gemm_trace": (C.c_int, [_P, C.c_int]),
     "smt_encode_operand_map": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int]),
     "smt_block_grad_gemm_grouped_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int64]),

@@ -357,12 +357,54 @@ def _workspace(nbytes: int, device, tag: str = "gemm") -> Optional[torch.Tensor]
     return buf
 
 
+_runs_cache: dict = {}
+LAST_SINGLE: dict = {}    # which kernel the last single-problem block_grad_gemm used (tests / reports)
+
+
+def _runs_for(index_list, block: int, device):
+    """Strip-sharing runs of an index list (cached per list object, validated by value): blocks grouped by block row,
+    columns ascending, cut into runs of at most `run width` blocks; b = 256 yields one run per 128-row half.
+    Returns (device tensor of smt_gemm_run, number of runs, fraction of the blocks that sit in a run of >= 2)."""
+    import numpy as np
+    snap = _snapshot_index_list(index_list)
+    key = (id(index_list), block, device)
+    hit = _runs_cache.get(key)
+    if hit is not None and hit[0] is snap:
+        return hit[1]
+    width = load().smt_block_grad_gemm_run_width(block)
+    by_row: dict = {}
+    for i, (r, c) in enumerate(snap):
+        by_row.setdefault(r, []).append((c, i))
+    rows, shared = [], 0
+    for r in sorted(by_row):
+        cols = sorted(by_row[r])
+        for k in range(0, len(cols), width):
+            part = cols[k:k + width]
+            if len(part) >= 2:
+                shared += len(part)
+            for half in ((0, 1) if block == 256 else (0,)):
+                cs = [c for c, _ in part] + [0] * (4 - len(part))
+                bs = [i for _, i in part] + [0] * (4 - len(part))
+                rows.append((r, half, len(part), *cs, *bs, 0))
+    arr = np.array(rows, dtype=np.int32).reshape(-1, 12)
+    assert arr.shape[1] * 4 == C.sizeof(_lib.GemmRun)
+    dev = torch.from_numpy(arr).to(device) if len(rows) else torch.empty((0, 12), dtype=torch.int32, device=device)
+    res = (dev, len(rows), shared / max(len(snap), 1))
+    if len(_runs_cache) > 4096:
+        _runs_cache.clear()
+    _runs_cache[key] = (snap, res)
+    return res
+
+
 def block_grad_gemm(x2d: torch.Tensor, dy2d: torch.Tensor, block_rc: torch.Tensor, block: int,
                     out: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None,
-                    accumulate: bool = False) -> torch.Tensor:
+                    accumulate: bool = False, index_list=None) -> torch.Tensor:
     """G[i*b+o, k] (+)= sum_t dy[t, r_i*b+o] * x[t, c_i*b+k]. smt.py:386-404.
 
     x2d: [T, in], dy2d: [T, out] (unit column stride, same dtype); block_rc: int32 [n, 2] on device.
+    `index_list` (optional): the host-side list `block_rc` was made from.  With it, 16-bit launches in which enough
+    blocks share a block row run the strip-sharing kernel (`smt_block_grad_gemm_runs`: the dy strip is fetched once per
+    run of up to 4 / 2 / 2 blocks for b = 64 / 128 / 256).  SMT_GEMM_RUNS=0 disables that, =2 forces it.
     """
     require_cuda(x2d, dy2d, block_rc)
     _req(x2d.dim() == 2 and dy2d.dim() == 2 and x2d.shape[0] == dy2d.shape[0],
@@ -380,6 +422,28 @@ def block_grad_gemm(x2d: torch.Tensor, dy2d: torch.Tensor, block_rc: torch.Tenso
          "out.is_contiguous() and out.numel() == n * block * block")
     lib = load()
     in_id = dtype_id(x2d.dtype)
+    import os
+    mode = os.environ.get("SMT_GEMM_RUNS", "1")
+    if index_list is not None and mode != "0" and n > 0 and T > 0 and x2d.dtype != torch.float32:
+        _req(len(index_list) == n, "len(index_list) == block_rc.shape[0]")
+        runs, n_runs, shared = _runs_for(index_list, block, x2d.device)
+        # Measured rule (profiles/r02_kernel_sweep.md): run tiles pay when the launch is big enough for the operand feed
+        # to matter (>= 148 blocks) and the runs are wide (singles are better off on the plain kernel's taller stages;
+        # two 80 KiB stages of a b = 256 pair tile cannot hide HBM latency).  Small launches are bound by fixed costs
+        # either way.
+        width = n / max(n_runs, 1)
+        if mode == "2" or (block != 256 and n >= 148 and width >= (2.0 if block == 64 else 1.5)):
+            ws_bytes = lib.smt_block_grad_gemm_runs_workspace_bytes(n_runs, block, T)
+            ws = _workspace(ws_bytes, x2d.device, tag="gemm_runs")
+            with _timed("block_grad_gemm", x2d.device, (n, block, T)):
+                check(lib.smt_block_grad_gemm_runs(ptr(x2d), x2d.stride(0), x2d.shape[1], ptr(dy2d), dy2d.stride(0),
+                                                   dy2d.shape[1], T, in_id, ptr(runs), n_runs, block, ptr(out),
+                                                   dtype_id(out.dtype), 1 if accumulate else 0, ptr(ws), ws_bytes,
+                                                   _st(x2d)), "smt_block_grad_gemm_runs")
+            _count(lib.smt_last_launch_count())
+            LAST_SINGLE.update(kernel="runs", runs=n_runs, shared_fraction=shared)
+            return out
+    LAST_SINGLE.update(kernel="blocks", runs=0, shared_fraction=0.0)
     ws_bytes = lib.smt_block_grad_gemm_workspace_bytes(n, block, T, in_id)
     ws = _workspace(ws_bytes, x2d.device)
     with _timed("block_grad_gemm", x2d.device, (n, block, T)):

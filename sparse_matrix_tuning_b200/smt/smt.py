@@ -233,11 +233,11 @@ def _block_weight_grad(sw_param, index_list, x2, dy2, b, out_dtype):
             _enqueue_block_grad(x2, dy2, index_list, sink, b, accumulate)   # grouped launch(es) per backward
         else:
             rc = _block_rc_for(index_list, dy2.device)
-            ops.block_grad_gemm(x2, dy2, rc, b, out=sink.view, accumulate=accumulate)
+            ops.block_grad_gemm(x2, dy2, rc, b, out=sink.view, accumulate=accumulate, index_list=index_list)
             sink.sq_ok = False
         return None
     rc = _block_rc_for(index_list, dy2.device)
-    return ops.block_grad_gemm(x2, dy2, rc, b, out_dtype=out_dtype).view(n * b, b)                # smt.py:382-404
+    return ops.block_grad_gemm(x2, dy2, rc, b, out_dtype=out_dtype, index_list=index_list).view(n * b, b)   # smt.py:382-404
 
 
 class LinearLayer_MatrixSparsity(nn.Module):

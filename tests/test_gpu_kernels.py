@@ -631,3 +631,68 @@ def test_fused_linear_rejects_unsupported_shapes(ops):
     assert not ops.fused_linear_supported([w_ok.float()])                                                      # fp32
     assert not ops.fused_linear_supported([w_ok] * 4)
     assert not ops.fused_linear_supported([w_ok, torch.zeros(256, 1024, device="cuda", dtype=torch.bfloat16)])
+
+
+# ---- strip-sharing run tiles ---------------------------------------------------------------------------------------------
+
+def _run_patterns(block):
+    nb = 1024 // block
+    full_rows = [(r, c) for r in (1, 2) for c in range(nb)]                      # clustered: whole block rows
+    mixed = [(0, 3), (0, 1), (3, 0), (0, 0), (2, 2), (0, 2), (3, 3), (1, 1), (3, 1), (0, nb - 1)][:max(4, nb)]
+    mixed = list(dict.fromkeys((r % nb, c % nb) for r, c in mixed))
+    return {"full_rows": full_rows, "mixed_unsorted": mixed, "single": [(nb - 1, nb - 1)]}
+
+
+@pytest.mark.parametrize("T", [1000, 4096])
+@pytest.mark.parametrize("block", [64, 128, 256])
+def test_block_grad_gemm_runs_vs_truth_and_block_tiles(ops, monkeypatch, block, T):
+    """Strip-sharing kernel (a tile = one block row x up to 4 / 2 / 2 of its blocks): against fp64 truth and against
+    the plain one-tile-per-block kernel, for whole block rows, an unsorted mixed list (runs + singles, output order =
+    list order) and a single block; ragged token counts; bf16 and fp32 outputs; accumulate."""
+    torch.manual_seed(block + T)
+    x = torch.randn(T, 1024).bfloat16()
+    dy = torch.randn(T, 1024).bfloat16()
+    xd, dyd = x.cuda(), dy.cuda()
+    for name, idx in _run_patterns(block).items():
+        rc = ops.make_block_rc(idx, "cuda")
+        truth = O.block_grad_truth(x.reshape(1, T, -1), dy.reshape(1, T, -1), idx, block)
+        scale = truth.abs().max().item()
+        monkeypatch.setenv("SMT_GEMM_RUNS", "2")                                 # force the run kernel
+        got32 = ops.block_grad_gemm(xd, dyd, rc, block, out_dtype=torch.float32, index_list=idx)
+        assert ops.LAST_SINGLE["kernel"] == "runs", name
+        assert (got32.cpu().double() - truth).abs().max().item() <= 3e-5 * scale, name
+        got16 = ops.block_grad_gemm(xd, dyd, rc, block, out_dtype=torch.bfloat16, index_list=idx)
+        assert (got16.cpu().double() - truth).abs().max().item() <= 2 ** -7 * scale, name
+        assert torch.equal(got32, ops.block_grad_gemm(xd, dyd, rc, block, out_dtype=torch.float32, index_list=idx))
+        base = torch.randn_like(got32)
+        acc = base.clone()
+        ops.block_grad_gemm(xd, dyd, rc, block, out=acc, accumulate=True, index_list=idx)
+        assert (acc - base - got32).abs().max().item() <= 3e-5 * scale, name
+        monkeypatch.setenv("SMT_GEMM_RUNS", "0")
+        plain = ops.block_grad_gemm(xd, dyd, rc, block, out_dtype=torch.float32, index_list=idx)
+        assert ops.LAST_SINGLE["kernel"] == "blocks"
+        assert (got32 - plain).abs().max().item() <= 3e-5 * scale, name           # different split points, same math
+    monkeypatch.delenv("SMT_GEMM_RUNS", raising=False)
+    # automatic choice: a big launch of wide runs => run tiles (b = 64 / 128); scattered singles / small launches => blocks
+    nb = 1024 // block
+    everything = [(r, c) for r in range(nb) for c in range(nb)]
+    ops.block_grad_gemm(xd, dyd, ops.make_block_rc(everything, "cuda"), block, index_list=everything)
+    assert ops.LAST_SINGLE["kernel"] == ("runs" if block == 64 else "blocks")     # 256 / 64 / 16 blocks: only b = 64 is big
+    diag = [(i, i) for i in range(min(4, 1024 // block))]
+    ops.block_grad_gemm(xd, dyd, ops.make_block_rc(diag, "cuda"), block, index_list=diag)
+    assert ops.LAST_SINGLE["kernel"] == "blocks"
+
+
+def test_block_grad_gemm_runs_many_tiles_no_split(ops, monkeypatch):
+    """More run tiles than SMs: several waves, no split-K, direct epilogue (b = 64, every block of a 2048 x 2048 weight)."""
+    torch.manual_seed(5)
+    T, b = 512, 64
+    x = torch.randn(T, 2048, device="cuda").bfloat16()
+    dy = torch.randn(T, 2048, device="cuda").bfloat16()
+    idx = [(r, c) for r in range(32) for c in range(32)]
+    monkeypatch.setenv("SMT_GEMM_RUNS", "2")
+    got = ops.block_grad_gemm(x, dy, ops.make_block_rc(idx, "cuda"), b, out_dtype=torch.float32, index_list=idx)
+    assert ops.LAST_SINGLE["kernel"] == "runs" and ops.LAST_SINGLE["runs"] == 256
+    ref = dy.float().t() @ x.float()
+    want = torch.stack([ref[r * b:(r + 1) * b, c * b:(c + 1) * b] for r, c in idx]).reshape(-1, b)
+    assert (got - want).abs().max().item() <= 2e-5 * want.abs().max().item()

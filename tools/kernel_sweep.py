@@ -43,8 +43,8 @@ def main():
     quick = "--quick" in sys.argv
     shapes = [(4096, 4096, "q 4096x4096"), (14336, 4096, "gate/up 14336x4096"), (4096, 14336, "down 4096x14336")]
     tokens = [2048, 8192, 16384] if not quick else [8192]
-    print("| weight [out x in] | b | sparsity | pattern | T | n | splits | us | TFLOP/s | of bf16 burst peak | roofline bound | of roofline |")
-    print("|---|---:|---:|---|---:|---:|---:|---:|---:|---:|---|---:|")
+    print("| weight [out x in] | b | sparsity | pattern | T | n | kernel | us | us (block tiles only) | us (run tiles forced) | TFLOP/s | of bf16 burst peak | roofline bound | of roofline |")
+    print("|---|---:|---:|---|---:|---:|---|---:|---:|---:|---:|---:|---|---:|")
     g = torch.Generator().manual_seed(1234)
     for fout, fin, label in shapes:
         for T in tokens:
@@ -64,15 +64,20 @@ def main():
                             idx = [(1, c) for c in range(n)]
                         rc = ops.make_block_rc(idx, "cuda")
                         out = torch.empty(n * b, b, device="cuda", dtype=torch.bfloat16)
-                        t = timeit(lambda: ops.block_grad_gemm(x, dy, rc, b, out=out))
+                        os.environ["SMT_GEMM_RUNS"] = "0"                       # round-1 kernel: one tile per block
+                        t_blocks = timeit(lambda: ops.block_grad_gemm(x, dy, rc, b, out=out, index_list=idx))
+                        os.environ["SMT_GEMM_RUNS"] = "2"
+                        t_runs = timeit(lambda: ops.block_grad_gemm(x, dy, rc, b, out=out, index_list=idx))
+                        os.environ["SMT_GEMM_RUNS"] = "1"                       # default: strip-sharing runs when they pay
+                        t = timeit(lambda: ops.block_grad_gemm(x, dy, rc, b, out=out, index_list=idx))
+                        kern = ops.LAST_SINGLE.get("kernel", "?")
                         flops = 2.0 * b * b * T * n
                         ur, uc = len({r for r, _ in idx}), len({c for _, c in idx})
                         min_bytes = 2.0 * T * b * (ur + uc) + n * b * b * 2
                         t_tensor = flops / (PEAKS["bf16_tflops"] * 1e12)
                         t_hbm = min_bytes / (PEAKS["hbm_gbs"] * 1e9)
                         bound = "tensor" if t_tensor >= t_hbm else "hbm"
-                        splits, _ = ops.block_grad_gemm_plan(n, b, T, torch.bfloat16)
-                        print(f"| {label} | {b} | {sp * 100:g}% | {pattern} | {T} | {n} | {splits} | {t * 1e6:.1f} | "
+                        print(f"| {label} | {b} | {sp * 100:g}% | {pattern} | {T} | {n} | {kern} | {t * 1e6:.1f} | {t_blocks * 1e6:.1f} | {t_runs * 1e6:.1f} | "
                               f"{flops / t / 1e12:.1f} | {flops / t / 1e12 / PEAKS['bf16_tflops']:.3f} | {bound} | "
                               f"{max(t_tensor, t_hbm) / t:.3f} |", flush=True)
             del x, dy
