@@ -428,11 +428,13 @@ def block_grad_gemm(x2d: torch.Tensor, dy2d: torch.Tensor, block_rc: torch.Tenso
         _req(len(index_list) == n, "len(index_list) == block_rc.shape[0]")
         runs, n_runs, shared = _runs_for(index_list, block, x2d.device)
         # Measured rule (profiles/r02_kernel_sweep.md): run tiles pay when the launch is big enough for the operand feed
-        # to matter (>= 148 blocks) and the runs are wide (singles are better off on the plain kernel's taller stages;
-        # two 80 KiB stages of a b = 256 pair tile cannot hide HBM latency).  Small launches are bound by fixed costs
-        # either way.
+        # to matter (>= 148 blocks), the runs are wide (singles are better off on the plain kernel's taller stages;
+        # two 80 KiB stages of a b = 256 pair tile cannot hide HBM latency) and the run tiles (times their one-wave
+        # split factor) still fill the GPU.  Small launches are bound by fixed costs either way.
         width = n / max(n_runs, 1)
-        if mode == "2" or (block != 256 and n >= 148 and width >= (2.0 if block == 64 else 1.5)):
+        sms = 148
+        fill = n_runs if n_runs >= sms else n_runs * (sms // max(n_runs, 1))      # CTAs of the (one-wave) split plan
+        if mode == "2" or (block != 256 and n >= 148 and width >= (2.0 if block == 64 else 1.5) and fill >= 120):
             ws_bytes = lib.smt_block_grad_gemm_runs_workspace_bytes(n_runs, block, T)
             ws = _workspace(ws_bytes, x2d.device, tag="gemm_runs")
             with _timed("block_grad_gemm", x2d.device, (n, block, T)):
