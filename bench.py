@@ -485,9 +485,15 @@ def run_ours(args):
     # ---- extra, before the model is converted: score-kernel rooflines and config-2 points (rank 0 only) -------------
     score_roof, cfg2, qkv_ab = None, None, None
     if not args.no_extra and rank == 0:
-        score_roof = score_kernel_rooflines(device, hbm_peak)
-        cfg2 = config2_points(device, peaks)
-        qkv_ab = fused_qkv_ab(device, T, peaks)
+        def guarded(fn, *a):                                      # an extra record must never cost the headline
+            try:
+                return fn(*a)
+            except Exception as e:
+                torch.cuda.empty_cache()
+                return {"error": f"{type(e).__name__}: {e}"}
+        score_roof = guarded(score_kernel_rooflines, device, hbm_peak)
+        cfg2 = guarded(config2_points, device, peaks)
+        qkv_ab = guarded(fused_qkv_ab, device, T, peaks)
     barrier()
 
     def convert(s_attn, s_mlp):
@@ -718,7 +724,9 @@ def run_ours(args):
         M.fuse_qkv_projections(model)
     # ---- cross-rank reductions of the timings ------------------------------------------------------------------------
     breakdown = {"phases": ["forward", "backward (incl. grouped block-grad GEMM chunks)", "exchange wait", "adam + zero_grad"],
-                 "mean_ms_this_rank": phase_mean, "host_flush_ms_per_step": host_flush_ms}
+                 "mean_ms_this_rank": phase_mean, "host_flush_ms_per_step": host_flush_ms,
+                 # activations (x, dy of every converted module) that the deferred grouped launch keeps alive until it runs
+                 "operand_bytes_held_until_flush_max": ops.HOST_TIME["operand_bytes_held_max"]}
     if world > 1:
         t = torch.tensor([ms_total, ms_e2e, ms_nockpt or 0.0, ms_unfused or 0.0], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -850,7 +858,7 @@ def run_ours(args):
                              "frac": (trainable * 30 / (adam_ms * 1e-3) / 1e9 / hbm_peak) if adam_ms else None,
                              "clip_norm_source": sq_source}}
     if score_roof:
-        also.update(score_roof)
+        also.update(score_roof if "error" not in score_roof else {"score_kernels": score_roof})
     if cfg2:
         also["config2"] = cfg2
     if qkv_ab:

@@ -26,6 +26,7 @@
 #include "common.cuh"
 #include "umma_ptx.cuh"
 #include "gemm_epilogue.cuh"
+#include "tma_host.cuh"
 
 namespace smt {
 namespace {
@@ -245,41 +246,8 @@ __global__ void __launch_bounds__(kRunThreads, 1) block_grad_runs_kernel(const _
 
 // ---- host side ------------------------------------------------------------------------------------------
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn runs_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (fn == nullptr) {
-    void* sym = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
-        qres != cudaDriverEntryPointSuccess)
-      return nullptr;
-    fn = reinterpret_cast<EncodeTiledFn>(sym);
-  }
-  return fn;
-}
-
 int encode_strip_map(CUtensorMap* map, const void* base, int64_t features, int64_t T, int64_t ld, int in_dtype, int ktile) {
-  EncodeTiledFn enc = runs_encode_fn();
-  if (!enc) {
-    set_error("smt_block_grad_gemm_runs: cuTensorMapEncodeTiled not available from the driver");
-    return SMT_ERR_CUDA;
-  }
-  const cuuint64_t gdim[2] = {(cuuint64_t)features, (cuuint64_t)T};
-  const cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
-  const cuuint32_t box[2] = {64, (cuuint32_t)ktile};
-  const cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, in_dtype == SMT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
-                   const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("smt_block_grad_gemm_runs: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-    return SMT_ERR_CUDA;
-  }
-  return SMT_OK;
+  return encode_2d_sw128(map, base, features, T, ld, in_dtype, ktile, "smt_block_grad_gemm_runs");
 }
 
 struct RunPlan {

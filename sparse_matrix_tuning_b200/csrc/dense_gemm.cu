@@ -23,6 +23,7 @@
 
 #include "common.cuh"
 #include "umma_ptx.cuh"
+#include "tma_host.cuh"
 
 namespace smt {
 namespace {
@@ -286,43 +287,10 @@ __global__ void __launch_bounds__(kDenseThreads, 1) fused_dense_umma_2sm_kernel(
 
 // ---- host side -------------------------------------------------------------------------------------------------
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn dense_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (fn == nullptr) {
-    void* sym = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
-        qres != cudaDriverEntryPointSuccess)
-      return nullptr;
-    fn = reinterpret_cast<EncodeTiledFn>(sym);
-  }
-  return fn;
-}
-
 // 2-D map over a row-major [rows, cols] 16-bit matrix (cols contiguous); box = {64 cols, box_rows}, 128-byte swizzle,
 // out-of-bounds elements read as zero.
 int encode_dense_map(CUtensorMap* map, const void* base, int64_t cols, int64_t rows, int64_t ld, int dtype, int box_rows) {
-  EncodeTiledFn enc = dense_encode_fn();
-  if (!enc) {
-    set_error("smt_fused_linear: cuTensorMapEncodeTiled not available from the driver");
-    return SMT_ERR_CUDA;
-  }
-  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  const cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
-  const cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
-  const cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, dtype == SMT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
-                   const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("smt_fused_linear: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-    return SMT_ERR_CUDA;
-  }
-  return SMT_OK;
+  return encode_2d_sw128(map, base, cols, rows, ld, dtype, box_rows, "smt_fused_linear");
 }
 
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

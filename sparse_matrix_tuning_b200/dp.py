@@ -75,12 +75,14 @@ class OverlappedGradExchange:
     `finish()` (before `optimizer.step()`) joins the side stream and hands the per-chunk sums of squares to the
     optimizer, so neither the exchange nor the clip norm leaves a serialized pass at the end of the step."""
 
-    def __init__(self, optimizer, group=None, sqnorm: bool = True):
+    def __init__(self, optimizer, group=None, sqnorm=None):
+        """`sqnorm`: None = compute the per-chunk sums of squares only when there is something to reduce (world > 1; on
+        one GPU the GEMM epilogue's own per-block sums are valid); True = always (tests); False = never."""
         from .smt import smt as _smt
         self._smt = _smt
         self.optimizer, self.group = optimizer, group
         self.ws = world_size(group)
-        self.sqnorm = sqnorm and self.ws > 1                # one GPU: the GEMM epilogue's own partial sums are used
+        self.sqnorm = (self.ws > 1) if sqnorm is None else bool(sqnorm)
         arenas = [a for a in optimizer._arenas if a is not None]
         if len(arenas) != 1 or not arenas[0].all_sinks:
             raise RuntimeError("OverlappedGradExchange needs an SMTAdam with one flat arena of SMT block parameters")

@@ -585,7 +585,8 @@ def compact_adam(master: torch.Tensor, exp_avg: torch.Tensor, exp_avg_sq: torch.
 # ---- grouped block-gradient GEMM: several (x, dy) problems in one launch ------------------------------------
 
 LAST_GROUP: dict = {}     # shape of the most recent grouped launch (bench.py reports it)
-HOST_TIME = {"flush_s": 0.0, "flushes": 0}   # host-side cost of building + launching grouped launches (bench.py)
+HOST_TIME = {"flush_s": 0.0, "flushes": 0, "operand_bytes_held_max": 0}   # host-side cost of grouped launches and the
+                                                                           # bytes of x / dy kept alive until a flush (bench.py)
 
 _ITEM_DT = None
 
@@ -671,6 +672,11 @@ class BlockGradBatch:
         t0 = time.perf_counter()
         problems, self.problems = self.problems, []
         self._out_ptrs = set()
+        held = {}
+        for pr in problems:                                   # distinct operands this batch kept alive until now
+            for t in (pr.x, pr.dy):
+                held[t.data_ptr()] = t.shape[0] * t.stride(0) * t.element_size()
+        HOST_TIME["operand_bytes_held_max"] = max(HOST_TIME["operand_bytes_held_max"], sum(held.values()))
         groups: dict = {}
         for pr in problems:
             if len(pr.idx) == 0 or pr.x.shape[0] == 0:

@@ -972,3 +972,56 @@ def test_fused_qkv_falls_back_when_called_out_of_pattern(api):
                       (k_other, ref(x_other, attn.k_proj.weight)), (v_alone, ref(x_other, attn.v_proj.weight))):
         assert (got.float() - want).abs().max().item() <= tol * want.abs().max().item()
     assert M.unfuse_qkv_projections(model) == 1 and "forward" not in attn.q_proj.__dict__
+
+
+def test_chunked_flush_and_overlapped_exchange_on_one_gpu(api):
+    """The data-parallel step's machinery with a world of one: the grouped block-gradient GEMM flushed in chunks DURING
+    backward (layer boundaries, chunk_blocks pending), every chunk handed to `OverlappedGradExchange` (side stream, per-chunk
+    sums of squares), the optimizer clipping with those partial norms.  Must equal the unchunked, exchange-free step."""
+    M, _H = api
+    from transformers import LlamaConfig, LlamaForCausalLM
+    from sparse_matrix_tuning_b200 import dp
+    from sparse_matrix_tuning_b200.optim import SMTAdam
+
+    def run(chunked):
+        torch.manual_seed(0)
+        cfg = LlamaConfig(vocab_size=512, hidden_size=512, intermediate_size=1024, num_hidden_layers=4,
+                          num_attention_heads=8, num_key_value_heads=4, max_position_embeddings=128)
+        model = LlamaForCausalLM(cfg).cuda().bfloat16()
+        sel = {("q_proj", 0): [(0, 1), (1, 0)], ("k_proj", 0): [(0, 0)], ("v_proj", 1): [(0, 1)],
+               ("q_proj", 2): [(1, 1), (0, 0), (0, 1)], ("k_proj", 3): [(0, 1)], ("q_proj", 3): [(1, 0)]}
+        M.freeze_unselected_matrix_layer(model, {}, sel)
+        M.convert_linear_layer_to_matrix_sparsity(model, {}, sel)
+        model.gradient_checkpointing_enable(gradient_checkpointing_kwargs={"use_reentrant": False})
+        model.enable_input_require_grads()
+        model.train()
+        opt = SMTAdam(M.get_optimizer_sparse_grouped_parameters(model, 0.0, 1e-3), betas=(0.9, 0.95), max_grad_norm=0.05)
+        M.set_grouped_backward(True, chunk_blocks=2 if chunked else 0)
+        ex = dp.OverlappedGradExchange(opt, sqnorm=True) if chunked else None
+        try:
+            ids = torch.randint(0, 512, (2, 96), generator=torch.Generator().manual_seed(1)).cuda()
+            chunks = []
+            if ex is not None:
+                M.add_flush_listener(lambda sinks: chunks.append(len(sinks)))
+            for _ in range(2):
+                opt.zero_grad()
+                model(input_ids=ids, labels=ids, use_cache=False).loss.backward()
+                if ex is not None:
+                    ex.finish()
+                    assert opt._arenas[0].sq_override is not None and opt._arenas[0].sq_override.numel() >= 2
+                grads = opt.flat_grads()[0].float().clone()
+                opt.step()
+                src = opt.sqnorm_source
+            params = torch.cat([p.detach().reshape(-1).float() for g in opt.param_groups for p in g["params"]])
+            return grads, params, src, chunks
+        finally:
+            if ex is not None:
+                ex.close()
+            M._flush_listeners.clear()
+            M.set_grouped_backward(False)
+
+    g0, p0, src0, _ = run(False)
+    g1, p1, src1, chunks = run(True)
+    assert src1 == "partials" and len(chunks) >= 4 and max(chunks) <= 4          # several flushes per backward pass
+    assert (g1 - g0).abs().max().item() <= 2 ** -7 * g0.abs().max().item()
+    assert (p1 - p0).abs().max().item() <= 2.1e-3 * 2                             # clip active (max_norm 0.05): same norm
