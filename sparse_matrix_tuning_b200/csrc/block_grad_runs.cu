@@ -10,7 +10,7 @@
 // side in shared memory, forming one UMMA B operand of N = ncols*b columns (b = 256: two N = 256 instructions that share
 // the A descriptor, one TMEM accumulator each):
 //
-//     b = 64   up to 4 blocks per tile   1 + 4 TMA boxes of 64 tokens per stage, 5 stages   M = 128 (upper half unused), N <= 256
+//     b = 64   up to 4 blocks per tile   1 + 4 TMA boxes of 96 tokens per stage, 3 stages   M = 128 (upper half unused), N <= 256
 //     b = 128  up to 2 blocks per tile   2 + 4 boxes of 64 tokens, 4 stages                 M = 128, N <= 256
 //     b = 256  up to 2 blocks per tile   2 + 8 boxes of 64 tokens, 2 stages                 M = 128 (one half of the block row), 2 x N = 256
 //              (two stages of 80 KiB cannot hide HBM latency: the host only takes this form for b = 256 when forced)
@@ -35,23 +35,29 @@ constexpr int kRunThreads = 64 + 32 * 8;        // warp 0 TMA, warp 1 MMA + TMEM
 constexpr int kRunEpiWarps = 8;
 constexpr size_t kRunCounterBytes = 16384;
 
-// Tokens per pipeline stage for b = 64 / 128.  64-token stages leave room for 5 / 4 stages (40 / 48 KiB each), which a
-// launch whose strips come from HBM needs to hide the load latency; 128-token stages halve the number of TMA boxes but
-// only two of them fit (measured: profiles/r02_runs_variants_raw.txt).
-#ifndef SMT_RUNS_KT_SMALL
-#define SMT_RUNS_KT_SMALL 64
+// Tokens per pipeline stage for b = 64 / 128 (measured: profiles/r02_runs_variants_raw.txt).  A launch whose strips
+// come from HBM needs >= 3 stages to hide the load latency, and every TMA box costs the producer ~70 clk whatever its
+// height - so the tallest box that still leaves 3-4 stages wins: b = 64: 96 tokens (5 boxes, 60 KiB, 3 stages: 115.6 us
+// on 716 blocks x T 8192, against 140.0 with 64-token and 119.6 with 80-token stages); b = 128: 64 tokens (6 boxes,
+// 48 KiB, 4 stages; 80 tokens x 3 stages measured the same).  128-token stages (two stages only) were no better than
+// the plain kernel.
+#ifndef SMT_RUNS_KT_64
+#define SMT_RUNS_KT_64 96       // b = 64
+#endif
+#ifndef SMT_RUNS_KT_128
+#define SMT_RUNS_KT_128 64      // b = 128
 #endif
 
 template <int B>
 struct RunCfg {
   static constexpr int NW = B == 64 ? 4 : 2;                 // blocks per run
-  static constexpr int KT = B == 256 ? 64 : SMT_RUNS_KT_SMALL;   // tokens per pipeline stage
+  static constexpr int KT = B == 256 ? 64 : (B == 128 ? SMT_RUNS_KT_128 : SMT_RUNS_KT_64);   // tokens per pipeline stage
   static constexpr int CHUNK = KT * 128;                     // one {64 features x KT tokens} TMA box
   static constexpr int A_LOAD = B == 64 ? 1 : 2;             // dy chunks (the M = 128 operand of b = 64 aliases the next chunk)
   static constexpr int B_PER_BLOCK = B / 64;
   static constexpr int B_MAX = NW * B_PER_BLOCK;             // 4, 4, 8
-  static constexpr int STAGE_BYTES = (A_LOAD + B_MAX) * CHUNK;   // 40 / 48 / 80 KiB with 64-token stages
-  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;      // 5 / 4 / 2
+  static constexpr int STAGE_BYTES = (A_LOAD + B_MAX) * CHUNK;   // 60 / 48 / 80 KiB
+  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;      // 3 / 4 / 2
   static constexpr int TILE_ROWS = B == 64 ? 64 : 128;       // output rows of one block that a tile produces
   static constexpr int SLOT = TILE_ROWS * B;                 // elements of one block's part of a tile
   static constexpr int TMEM_COLS = B == 256 ? 512 : 256;
@@ -254,7 +260,7 @@ struct RunPlan {
   int splits, kt_total, kt_per_split;
 };
 
-int run_ktile(int block) { return block == 256 ? 64 : SMT_RUNS_KT_SMALL; }
+int run_ktile(int block) { return block == 256 ? 64 : (block == 128 ? SMT_RUNS_KT_128 : SMT_RUNS_KT_64); }
 int run_width(int block) { return block == 64 ? 4 : 2; }
 int run_slot(int block) { return (block == 64 ? 64 : 128) * block; }
 

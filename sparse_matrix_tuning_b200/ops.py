@@ -434,7 +434,7 @@ def block_grad_gemm(x2d: torch.Tensor, dy2d: torch.Tensor, block_rc: torch.Tenso
         width = n / max(n_runs, 1)
         sms = 148
         fill = n_runs if n_runs >= sms else n_runs * (sms // max(n_runs, 1))      # CTAs of the (one-wave) split plan
-        if mode == "2" or (block != 256 and n >= 148 and width >= (2.0 if block == 64 else 1.5) and fill >= 120):
+        if mode == "2" or (block != 256 and n >= 148 and width >= (2.0 if block == 64 else 1.5) and fill >= 80):
             ws_bytes = lib.smt_block_grad_gemm_runs_workspace_bytes(n_runs, block, T)
             ws = _workspace(ws_bytes, x2d.device, tag="gemm_runs")
             with _timed("block_grad_gemm", x2d.device, (n, block, T)):
