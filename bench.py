@@ -67,6 +67,8 @@ def parse_args():
     ap.add_argument("--no-overlap", action="store_true", help="N>1: one blocking all-reduce after backward (round-1 behaviour)")
     ap.add_argument("--chunk-blocks", type=int, default=440, help="grouped GEMM flush granularity during backward (N>1)")
     ap.add_argument("--capture-steps", type=int, default=4, help="gradient-capture passes of the warm-up phase")
+    ap.add_argument("--torch-profile", type=str, default="", help="(diagnostic) write a torch.profiler kernel table of two "
+                                                                  "steps to this file: GPU busy time vs step time")
     return ap.parse_args()
 
 
@@ -692,6 +694,21 @@ def run_ours(args):
     params_identical = dp.replicas_identical(opt) if world > 1 else None
     if world > 1 and not params_identical:
         sys.stderr.write(f"[bench] rank {rank}: replicas DIVERGED: flat parameters / fp32 masters differ between ranks\n")
+    if args.torch_profile and rank == 0:
+        from torch.profiler import ProfilerActivity, profile
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+            t0 = time.perf_counter()
+            for i in range(2):
+                step(dev_ids[args.warmup + i])
+            torch.cuda.synchronize()
+            wall = (time.perf_counter() - t0) * 1e3
+        ka = prof.key_averages()
+        busy = sum(e.self_device_time_total for e in ka) / 1e3
+        with open(args.torch_profile, "w") as f:
+            f.write(f"two steps: wall {wall:.1f} ms (under the profiler), sum of device kernel time {busy:.1f} ms "
+                    f"=> GPU busy {100 * busy / wall:.1f} %\n\n")
+            f.write(ka.table(sort_by="device_time_total", row_limit=40))
     # ---- extra (reported, not the headline): the same step WITHOUT activation recomputation ------------------------
     ms_nockpt = None
     if not args.no_ckpt and not args.no_extra:
