@@ -1025,3 +1025,33 @@ def test_chunked_flush_and_overlapped_exchange_on_one_gpu(api):
     assert src1 == "partials" and len(chunks) >= 4 and max(chunks) <= 4          # several flushes per backward pass
     assert (g1 - g0).abs().max().item() <= 2 ** -7 * g0.abs().max().item()
     assert (p1 - p0).abs().max().item() <= 2.1e-3 * 2                             # clip active (max_norm 0.05): same norm
+
+
+def test_many_small_blocks_through_the_api_use_run_tiles_and_match_the_reference_loop(api, monkeypatch):
+    """b = 64 with every block of a 1024 x 1024 weight selected (256 blocks, 16 per block row): `linearZ.backward` takes
+    the strip-sharing run kernel on its own (per-module launch) and must still reproduce the reference's per-block loop
+    (oracle.linearz_backward restates smt.py:376-413) - no worse than the reference's own bf16 error vs fp64 truth."""
+    M, _H = api
+    from sparse_matrix_tuning_b200 import ops
+    monkeypatch.setattr(M, "Block_dimension", 64)
+    torch.manual_seed(2)
+    b, nb = 64, 16
+    idx = [(r, c) for r in range(nb) for c in range(nb)]
+    torch.Generator().manual_seed(0)
+    perm = torch.randperm(len(idx)).tolist()
+    idx = [idx[i] for i in perm]                                   # list order = compact row order, not sorted
+    w = (torch.randn(1024, 1024) * 0.02).bfloat16()
+    x = torch.randn(2, 256, 1024).bfloat16()
+    dy = torch.randn(2, 256, 1024).bfloat16()
+    layer = M.LinearLayer_MatrixSparsity(torch.nn.Parameter(w.clone().cuda()), index_list=idx)
+    xin = x.cuda().requires_grad_(True)
+    layer(xin).backward(dy.cuda())
+    assert ops.LAST_SINGLE["kernel"] == "runs"
+    got = layer.selected_weight.grad.detach().cpu()
+    truth = O.block_grad_truth(x, dy, idx, b)
+    _gi, ref = O.linearz_backward(x, dy, w, idx, b)
+    scale = truth.abs().max().item()
+    err = (got.double() - truth).abs().max().item() / scale
+    ref_err = (ref.double() - truth).abs().max().item() / scale
+    assert err <= 2 ** -7 and err <= ref_err * 1.10 + 1e-6, (err, ref_err)
+    assert (xin.grad.float().cpu() - _gi.float()).abs().max().item() <= 2 ** -6 * _gi.float().abs().max().item()

@@ -1,6 +1,8 @@
 """A/B of the split-K reduction of the block-gradient GEMM: thread-block cluster + DSMEM (default) vs the global
 workspace paths (SMT_GEMM_CLUSTER_REDUCE=0), on per-module launches of BASELINE config 2 (b = 256 and smaller blocks).
-CUDA events, 256 MB memset between iterations, median of 9.  Measurement tooling."""
+CUDA events, 256 MB memset between iterations, median of 9.  Measurement tooling for an experiment that was NOT kept: the
+`SMT_GEMM_CLUSTER_REDUCE` switch only exists with `profiles/r02_cluster_dsmem_reduce_experiment.patch` applied (results:
+`profiles/r02_cluster_dsmem_reduce.md`)."""
 import os
 import sys
 
