@@ -135,6 +135,39 @@ def set_grouped_backward(enabled: bool, chunk_blocks: int = 0) -> None:
     _grouped["chunk_blocks"] = int(chunk_blocks) if enabled else 0
 
 
+def suggest_chunk_blocks(model, min_chunks: int = 2, sm_pairs: int = 74) -> int:
+    """`chunk_blocks` for `set_grouped_backward` that cuts the backward pass of `model` into at least `min_chunks`
+    grouped launches while wasting as few rounds of the cta_group::2 kernel as possible (a launch of n blocks takes
+    ceil(ceil(n / 2) / sm_pairs) rounds of two-block tiles; flushes only happen at layer boundaries, in backward order).
+    Returns 0 (one launch per backward pass) when the model has too few blocks to fill two launches."""
+    per_layer: Dict[int, int] = {}
+    for name, mod in model.named_modules():
+        if isinstance(mod, LinearLayer_MatrixSparsity):
+            layer = _layer_of(name + ".")
+            per_layer[layer if layer is not None else -1] = per_layer.get(layer if layer is not None else -1, 0) + \
+                len(mod.index_list)
+    counts = [per_layer[k] for k in sorted(per_layer, reverse=True)]           # backward visits the last layer first
+    total = sum(counts)
+    rounds = lambda n: -(-(-(-n // 2)) // sm_pairs)
+    if total < 4 * sm_pairs * min_chunks:
+        return 0
+    best = (None, 0)
+    for t in sorted({sum(counts[:k]) for k in range(1, len(counts))}):
+        chunks, pending = [], 0
+        for c in counts:                                                     # flush BEFORE adding the next layer's blocks
+            if pending >= t:
+                chunks.append(pending)
+                pending = 0
+            pending += c
+        chunks.append(pending)
+        if len(chunks) < min_chunks:
+            continue
+        cost = (sum(rounds(c) for c in chunks), -len(chunks))
+        if best[0] is None or cost < best[0]:
+            best = (cost, t)
+    return best[1]
+
+
 def add_flush_listener(fn) -> None:
     """`fn(sinks)` is called after every grouped launch with the GradSinks it delivered to (on the thread and the
     stream that launched it)."""
