@@ -103,10 +103,17 @@ class OverlappedGradExchange:
         self.keep_local = None      # debug (bench.py's dp_check): a tensor like `flat` that receives this rank's gradients
                                     # as they were BEFORE each chunk was reduced
         optimizer.grad_scale = 1.0 / self.ws
+        self._finished_at = -1                               # optimizer.steps_done at the last finish()
         _smt.add_flush_listener(self._on_flush)
+        # `optimizer.step()` joins the exchange by itself if the loop did not call finish() (idempotent per step)
+        self._hook = optimizer.register_step_pre_hook(lambda _opt, _a, _k: self.finish()) \
+            if hasattr(optimizer, "register_step_pre_hook") else None
 
     def close(self) -> None:
         self._smt.remove_flush_listener(self._on_flush)
+        if self._hook is not None:
+            self._hook.remove()
+            self._hook = None
 
     def _ranges(self, sinks):
         spans = sorted(((sk.view.data_ptr() - self._base) // self._esize, sk.view.numel()) for sk in sinks)
@@ -156,6 +163,11 @@ class OverlappedGradExchange:
     def finish(self) -> None:
         """Join the exchange: after this the flat gradient buffer holds the cross-rank SUM on the current stream and the
         optimizer knows the partial sums of squares.  Call between backward and `optimizer.step()`."""
+        if not self.active:
+            return                                           # exchange suspended (accumulation micro-batch / local-only step)
+        serial = getattr(self.optimizer, "steps_done", None)
+        if serial is not None and serial == self._finished_at and len(self._smt._pending) == 0 and not self._reduced:
+            return                                           # already joined for this gradient state
         self._smt.flush_block_grads()                        # last chunk (normally already flushed by the engine callback)
         if self.cuda:
             torch.cuda.current_stream(self.flat.device).wait_stream(self.side)
@@ -176,6 +188,7 @@ class OverlappedGradExchange:
         self._n_chunks = 0
         self._reduced = set()
         self.reduced_ranges = []
+        self._finished_at = serial if serial is not None else -1
 
 
 def allreduce_block_sums(accumulator, group=None) -> None:

@@ -191,6 +191,7 @@ class SMTAdam(torch.optim.Optimizer):
         super().__init__(params, defaults)
         self.max_grad_norm = float(max_grad_norm)
         self.grad_scale = float(grad_scale)                # e.g. 1/world_size after a SUM all-reduce
+        self.steps_done = 0                                # serial number of the gradient state (bumped by every step())
         self.flatten = bool(flatten)
         self._arenas: List[Optional[_Arena]] = []
         for group in self.param_groups:
@@ -352,6 +353,7 @@ class SMTAdam(torch.optim.Optimizer):
                 for p in group["params"]:
                     if p.grad is not None:
                         self._step_loose(p, common)
+        self.steps_done += 1
         for arena in self._arenas:
             if arena is not None:                            # the step consumed this gradient state
                 arena.sq_override = None

@@ -1003,14 +1003,15 @@ def test_chunked_flush_and_overlapped_exchange_on_one_gpu(api):
             chunks = []
             if ex is not None:
                 M.add_flush_listener(lambda sinks: chunks.append(len(sinks)))
-            for _ in range(2):
+            for it in range(2):
                 opt.zero_grad()
                 model(input_ids=ids, labels=ids, use_cache=False).loss.backward()
-                if ex is not None:
+                if ex is not None and it == 0:
                     ex.finish()
+                    ex.finish()                                    # idempotent: joining twice reduces nothing twice
                     assert opt._arenas[0].sq_override is not None and opt._arenas[0].sq_override.numel() >= 2
                 grads = opt.flat_grads()[0].float().clone()
-                opt.step()
+                opt.step()                                         # (second iteration: step() joins the exchange itself)
                 src = opt.sqnorm_source
             params = torch.cat([p.detach().reshape(-1).float() for g in opt.param_groups for p in g["params"]])
             return grads, params, src, chunks
