@@ -135,22 +135,32 @@ def set_grouped_backward(enabled: bool, chunk_blocks: int = 0) -> None:
     _grouped["chunk_blocks"] = int(chunk_blocks) if enabled else 0
 
 
-def suggest_chunk_blocks(model, min_chunks: int = 2, sm_pairs: int = 74) -> int:
+def suggest_chunk_blocks(model, min_chunks: int = 2, sm_pairs: int = 74, round_ms: float = 0.105,
+                         exposed_ms_per_block: float = 0.0019) -> int:
     """`chunk_blocks` for `set_grouped_backward` that cuts the backward pass of `model` into at least `min_chunks`
-    grouped launches while wasting as few rounds of the cta_group::2 kernel as possible (a launch of n blocks takes
-    ceil(ceil(n / 2) / sm_pairs) rounds of two-block tiles; flushes only happen at layer boundaries, in backward order).
-    Returns 0 (one launch per backward pass) when the model has too few blocks to fill two launches."""
+    grouped launches at the smallest cost for a data-parallel step:
+
+        cost = (rounds of the cta_group::2 kernel over all launches) * round_ms + (blocks of the LAST chunk) * exposed_ms_per_block
+
+    A launch of n blocks takes ceil(ceil(n / 2) / sm_pairs) rounds of two-block tiles (0.105 ms each at T = 8192), so many
+    small chunks waste rounds; the last chunk is flushed when the backward pass ends, so its all-reduce cannot hide behind
+    anything (measured on 2 and 8 B200: 1.6 ms for the whole 869-block buffer, profiles/r02_scaling_breakdown.md).  Flushes
+    only happen at layer boundaries, in backward order.  Returns 0 (one launch per backward pass) when the model has too few
+    blocks to fill two launches."""
     per_layer: Dict[int, int] = {}
     for name, mod in model.named_modules():
         if isinstance(mod, LinearLayer_MatrixSparsity):
             layer = _layer_of(name + ".")
-            per_layer[layer if layer is not None else -1] = per_layer.get(layer if layer is not None else -1, 0) + \
-                len(mod.index_list)
+            key = layer if layer is not None else -1
+            per_layer[key] = per_layer.get(key, 0) + len(mod.index_list)
     counts = [per_layer[k] for k in sorted(per_layer, reverse=True)]           # backward visits the last layer first
     total = sum(counts)
-    rounds = lambda n: -(-(-(-n // 2)) // sm_pairs)
     if total < 4 * sm_pairs * min_chunks:
         return 0
+
+    def rounds(n: int) -> int:
+        return -(-(-(-n // 2)) // sm_pairs)
+
     best = (None, 0)
     for t in sorted({sum(counts[:k]) for k in range(1, len(counts))}):
         chunks, pending = [], 0
@@ -162,7 +172,7 @@ def suggest_chunk_blocks(model, min_chunks: int = 2, sm_pairs: int = 74) -> int:
         chunks.append(pending)
         if len(chunks) < min_chunks:
             continue
-        cost = (sum(rounds(c) for c in chunks), -len(chunks))
+        cost = sum(rounds(c) for c in chunks) * round_ms + chunks[-1] * exposed_ms_per_block
         if best[0] is None or cost < best[0]:
             best = (cost, t)
     return best[1]
