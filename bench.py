@@ -65,8 +65,7 @@ def parse_args():
     ap.add_argument("--no-fuse-qkv", action="store_true", help="keep one library GEMM per q/k/v module instead of the fused "
                                                                "tcgen05 projection / input-gradient kernels")
     ap.add_argument("--no-overlap", action="store_true", help="N>1: one blocking all-reduce after backward (round-1 behaviour)")
-    ap.add_argument("--chunk-blocks", type=int, default=-1, help="grouped GEMM flush granularity during backward (N>1); "
-                                                                 "-1 = smt.suggest_chunk_blocks(model)")
+    ap.add_argument("--chunk-blocks", type=int, default=192, help="grouped GEMM flush granularity during backward (N>1)")
     ap.add_argument("--capture-steps", type=int, default=4, help="gradient-capture passes of the warm-up phase")
     ap.add_argument("--torch-profile", type=str, default="", help="(diagnostic) write a torch.profiler kernel table of two "
                                                                   "steps to this file: GPU busy time vs step time")
@@ -511,8 +510,6 @@ def run_ours(args):
     n_blocks = sum(len(v) for v in sel.values())
     trainable = opt.trainable_elements()
     overlap = world > 1 and not args.no_overlap and not args.no_group
-    if args.chunk_blocks < 0:
-        args.chunk_blocks = M.suggest_chunk_blocks(model)          # fewest wasted GEMM rounds for >= 2 chunks
     M.set_grouped_backward(not args.no_group, chunk_blocks=args.chunk_blocks if overlap else 0)
     exchange = dp.OverlappedGradExchange(opt) if overlap else None
     torch.cuda.empty_cache()
@@ -785,7 +782,7 @@ def run_ours(args):
             opt5 = convert(s5a, s5m)
             if not args.no_fuse_qkv:
                 M.fuse_qkv_projections(model)
-            M.set_grouped_backward(not args.no_group, chunk_blocks=M.suggest_chunk_blocks(model) if overlap else 0)
+            M.set_grouped_backward(not args.no_group, chunk_blocks=args.chunk_blocks if overlap else 0)
             ex5 = dp.OverlappedGradExchange(opt5) if overlap else None
 
             def step5(ids):

@@ -129,53 +129,14 @@ def set_grouped_backward(enabled: bool, chunk_blocks: int = 0) -> None:
     chunk_blocks = 0: ONE launch per backward pass (when the autograd engine finishes).
     chunk_blocks > 0: additionally flush DURING the backward pass, at a layer boundary (a module with a different
     input arrives), whenever at least that many blocks are pending - each chunk still fills the GPU (choose >= 148
-    tiles) and a data-parallel exchange can all-reduce it while the rest of the backward pass runs (dp.py)."""
+    tiles) and a data-parallel exchange can all-reduce it while the rest of the backward pass runs (dp.py).
+    Measured on 2 / 8 B200 (profiles/r02_scaling_breakdown.md): ~192 (three chunks of the 869-block selection) is the
+    sweet spot - the NCCL kernels only get SMs in the gaps between the backward pass's kernels, so chunks must be
+    flushed EARLY to be reduced by the time backward ends; two big chunks (284 / 504) left 1.4-2.7 ms exposed, three
+    small ones 0.3 ms, at the price of one more 0.1 ms round of the GEMM."""
     flush_block_grads()
     _grouped["enabled"] = bool(enabled)
     _grouped["chunk_blocks"] = int(chunk_blocks) if enabled else 0
-
-
-def suggest_chunk_blocks(model, min_chunks: int = 2, sm_pairs: int = 74, round_ms: float = 0.105,
-                         exposed_ms_per_block: float = 0.0019) -> int:
-    """`chunk_blocks` for `set_grouped_backward` that cuts the backward pass of `model` into at least `min_chunks`
-    grouped launches at the smallest cost for a data-parallel step:
-
-        cost = (rounds of the cta_group::2 kernel over all launches) * round_ms + (blocks of the LAST chunk) * exposed_ms_per_block
-
-    A launch of n blocks takes ceil(ceil(n / 2) / sm_pairs) rounds of two-block tiles (0.105 ms each at T = 8192), so many
-    small chunks waste rounds; the last chunk is flushed when the backward pass ends, so its all-reduce cannot hide behind
-    anything (measured on 2 and 8 B200: 1.6 ms for the whole 869-block buffer, profiles/r02_scaling_breakdown.md).  Flushes
-    only happen at layer boundaries, in backward order.  Returns 0 (one launch per backward pass) when the model has too few
-    blocks to fill two launches."""
-    per_layer: Dict[int, int] = {}
-    for name, mod in model.named_modules():
-        if isinstance(mod, LinearLayer_MatrixSparsity):
-            layer = _layer_of(name + ".")
-            key = layer if layer is not None else -1
-            per_layer[key] = per_layer.get(key, 0) + len(mod.index_list)
-    counts = [per_layer[k] for k in sorted(per_layer, reverse=True)]           # backward visits the last layer first
-    total = sum(counts)
-    if total < 4 * sm_pairs * min_chunks:
-        return 0
-
-    def rounds(n: int) -> int:
-        return -(-(-(-n // 2)) // sm_pairs)
-
-    best = (None, 0)
-    for t in sorted({sum(counts[:k]) for k in range(1, len(counts))}):
-        chunks, pending = [], 0
-        for c in counts:                                                     # flush BEFORE adding the next layer's blocks
-            if pending >= t:
-                chunks.append(pending)
-                pending = 0
-            pending += c
-        chunks.append(pending)
-        if len(chunks) < min_chunks:
-            continue
-        cost = sum(rounds(c) for c in chunks) * round_ms + chunks[-1] * exposed_ms_per_block
-        if best[0] is None or cost < best[0]:
-            best = (cost, t)
-    return best[1]
 
 
 def add_flush_listener(fn) -> None:

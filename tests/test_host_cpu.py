@@ -267,40 +267,3 @@ def test_block_budget_helpers_match_the_reference_golden():
     assert H.num_total_blocks(big) == 122528 and H.block_budget(big, 0.0071) == 869 and H.block_budget(big, 0.0086) == 1053
     assert H.targeted_module_dims(big)["k_proj"] == [1024, 4096]
 
-
-def test_suggest_chunk_blocks_prefers_a_small_last_chunk():
-    """Flush policy of the overlapped data-parallel step: wasted GEMM rounds vs the all-reduce of the LAST chunk, which
-    nothing can hide.  Host logic only (no kernels): fake converted modules with given block counts per layer."""
-    from sparse_matrix_tuning_b200.smt import smt as M
-
-    class Fake(M.LinearLayer_MatrixSparsity):
-        def __init__(self, n):
-            torch.nn.Module.__init__(self)
-            self.index_list = [(0, 0)] * n
-
-    def model(counts):
-        root = torch.nn.Module()
-        root.model = torch.nn.Module()
-        root.model.layers = torch.nn.ModuleList()
-        for c in counts:
-            layer = torch.nn.Module()
-            layer.self_attn = torch.nn.Module()
-            layer.self_attn.q_proj = Fake(c)
-            root.model.layers.append(layer)
-        return root
-
-    def chunks_for(counts, t):
-        out, pending = [], 0
-        for c in counts[::-1]:                       # backward order
-            if t and pending >= t:
-                out.append(pending)
-                pending = 0
-            pending += c
-        return out + [pending]
-
-    counts = [120, 100, 95, 90, 80, 75, 70, 60, 55, 50, 45, 29]           # 869 blocks, concentrated in the first layers
-    t = M.suggest_chunk_blocks(model(counts))
-    ch = chunks_for(counts, t)
-    assert len(ch) >= 2 and sum(ch) == 869 and ch[-1] <= 220              # the unhidden tail is small
-    assert M.suggest_chunk_blocks(model([10, 12, 9])) == 0                # too few blocks to fill two launches
-    assert M.suggest_chunk_blocks(model(counts), exposed_ms_per_block=0.0) in {sum(counts[::-1][:k]) for k in range(1, 12)}
