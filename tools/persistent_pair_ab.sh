@@ -1,6 +1,7 @@
 #!/bin/bash
 # On the GPU box: the in-step grouped block-gradient launch with the per-tile cta_group::2 kernel (SMT_GEMM_2SM=1) vs the
-# persistent form (SMT_GEMM_2SM=2), alternating, CUDA-event times from bench.py.  Experiment tooling.
+# persistent form (SMT_GEMM_2SM=2; only with profiles/r02_2sm_persistent_pair_tile.patch applied), alternating, CUDA-event
+# times from bench.py.  Experiment tooling (results: profiles/r02_ncu_summary.md).
 cd "$(dirname "$0")/.."
 CMD="python bench.py --steps 8 --warmup 3 --no-extra --no-cpu-baseline --capture-steps 1"
 for i in 1 2; do
