@@ -1,6 +1,7 @@
 """Tiny end-to-end pass over every kernel for compute-sanitizer (memcheck): small shapes, all code paths
 (whole/half-block tiles, fused and separate split-K reduction, grouped launch, fp32 path, Adam with write-back,
-top-k shared/global sort, gather/scatter, score kernels)."""
+top-k shared/global sort, gather/scatter, score kernels; run tiles, per-item overwrite + sums of squares, channel gradient,
+fused dense GEMMs, Adam with partial norms)."""
 import os
 import sys
 
@@ -57,5 +58,32 @@ ops.channel_score_reduce(a2, "L1")
 sc = torch.rand(30000, device=dev)
 ops.topk_blocks(sc, [0, 30000], [100])
 ops.topk_blocks(sc, [0, 10000, 30000], [9000, 17])
+# round-2 kernels: per-item overwrite + sums of squares, run tiles, channel gradient, fused dense GEMMs, Adam with partials
+for b in (64, 128, 256):
+    T, fin = 300, 1024
+    x = torch.randn(T, fin, device=dev).bfloat16()
+    dy = torch.randn(T, fin, device=dev).bfloat16()
+    nb = fin // b
+    idx = [(r, c) for r in range(min(nb, 3)) for c in range(nb)]
+    rc = ops.make_block_rc(idx, dev)
+    os.environ["SMT_GEMM_RUNS"] = "2"
+    got = ops.block_grad_gemm(x, dy, rc, b, out_dtype=torch.float32, index_list=idx)
+    os.environ["SMT_GEMM_RUNS"] = "1"
+    ref = dy.float()[:, :b].t() @ x.float()[:, :b]
+    assert (got[:b] - ref).abs().max() <= 3e-5 * ref.abs().max()
+    flat = torch.zeros(len(idx) * b * b, device=dev, dtype=torch.bfloat16)
+    sqp = torch.zeros(2 * len(idx), device=dev)
+    batch = ops.BlockGradBatch()
+    batch.add(x, dy, idx, flat.view(-1, b), b, accumulate=False, sq=sqp, sq_slot0=0)
+    batch.flush(accumulate=True)
+xq = torch.randn(300, 512, device=dev).bfloat16()
+ws = [torch.randn(n, 512, device=dev).bfloat16() for n in (512, 256, 256)]
+ys = ops.fused_linear_forward(xq, ws)
+dx = ops.fused_linear_dgrad([torch.randn_like(y) for y in ys], ws)
+cidx = ops.make_channel_idx([3, 70, 500], dev, pad_to=8)
+part = ops.channel_gather(xq, cidx)
+ops.channel_grad_gemm(part, 3, torch.randn(300, 256, device=dev).bfloat16())
+ops.compact_adam(*st, g, lr=1e-3, beta1=0.9, beta2=0.95, eps=1e-8, weight_decay=0.0, step=2,
+                 sqnorm=torch.rand(300, device=dev), max_norm=1.0)
 torch.cuda.synchronize()
 print("sanitize_small: ok")
