@@ -172,3 +172,68 @@ def test_grouped_launch_at_llama_scale_properties(ops):
         ref = dy[:, r * b:(r + 1) * b].float().t() @ x[:, c * b:(c + 1) * b].float()
         i = len(idx) // 2
         assert (Gm[i * b:(i + 1) * b] - ref).abs().max().item() <= 2e-5 * scale
+
+
+def test_grouped_launch_with_attention_and_mlp_blocks_at_llama_scale(ops):
+    """BASELINE config 5 shape: 1 052 blocks spread over attention (4096 x 4096, 1024 x 4096) AND MLP weights (gate/up
+    14336 x 4096 read the same input, down 4096 x 14336 has its own 14336-wide input), T = 4096 tokens, ONE grouped launch
+    with per-block sums of squares and a mix of overwriting and accumulating modules.  Size-independent properties:
+    determinism, token additivity, sums of squares = what is stored, spot checks of every module kind vs torch fp32."""
+    torch.manual_seed(3)
+    T, b = 4096, 256
+    g = torch.Generator().manual_seed(9)
+    x_attn = [torch.randn(T, 4096, device="cuda").bfloat16() for _ in range(3)]       # q/k/v of a layer share it
+    x_mlp = [torch.randn(T, 4096, device="cuda").bfloat16() for _ in range(3)]        # gate/up of a layer share it
+    x_down = [torch.randn(T, 14336, device="cuda").bfloat16() for _ in range(3)]
+    specs = []
+    for layer in range(3):
+        specs += [(4096, x_attn[layer], 70), (1024, x_attn[layer], 25), (1024, x_attn[layer], 25),
+                  (14336, x_mlp[layer], 80), (14336, x_mlp[layer], 80), (4096, x_down[layer], 70)]
+    specs[-1] = (4096, x_down[2], 72)                                                  # 1 052 blocks in total
+    mods, total = [], 0
+    for m, (fo, x, n) in enumerate(specs):
+        fi = x.shape[1]
+        perm = torch.randperm((fo // b) * (fi // b), generator=g)[:n].tolist()
+        idx = [(p // (fi // b), p % (fi // b)) for p in perm]
+        dy = torch.randn(T, fo, device="cuda").bfloat16()
+        mods.append((x, dy, idx, total, m % 2 == 0))                                   # every other module overwrites
+        total += n * b * b
+    n_blocks = total // (b * b)
+    assert n_blocks == 1052
+    init = torch.randn(total, device="cuda")
+
+    def run(t0, t1, with_sq=True):
+        out = init.clone()
+        sq = torch.full((2 * n_blocks,), -1.0, device="cuda") if with_sq else None
+        batch = ops.BlockGradBatch()
+        for x, dy, idx, off, overwrite in mods:
+            batch.add(x[t0:t1], dy[t0:t1], idx, out[off:off + len(idx) * b * b].view(-1, b), b, accumulate=not overwrite,
+                      sq=sq, sq_slot0=2 * (off // (b * b)) if with_sq else -1)
+        assert batch.flush(accumulate=True) == 1
+        return out, sq
+
+    G, sq = run(0, T)
+    assert ops.LAST_GROUP["cta_group_2"] and ops.LAST_GROUP["emits_sq"]
+    G2, sq2 = run(0, T)
+    assert torch.equal(G, G2) and torch.equal(sq, sq2)                                 # deterministic
+    want_sq = (G.view(n_blocks, 2, -1).double() ** 2).sum(-1).reshape(-1)
+    assert torch.allclose(sq.double(), want_sq, rtol=1e-5, atol=0)
+    scale = (G - init).abs().max().item()
+    h = T // 2 + 64
+    Ga, _ = run(0, h, with_sq=False)
+    Gb, _ = run(h, T, with_sq=False)
+    for x, dy, idx, off, overwrite in mods:                                            # additivity over tokens
+        sl = slice(off, off + len(idx) * b * b)
+        base = 0.0 if overwrite else init[sl]
+        lhs = G[sl] - base
+        rhs = (Ga[sl] - base) + (Gb[sl] - base)
+        assert (lhs - rhs).abs().max().item() <= 2e-5 * scale
+    for m in (0, 1, 3, 5, 17):                                                         # q, k, gate, down, last down
+        x, dy, idx, off, overwrite = mods[m]
+        i = len(idx) // 2
+        r, c = idx[i]
+        ref = dy[:, r * b:(r + 1) * b].float().t() @ x[:, c * b:(c + 1) * b].float()
+        got = G[off + i * b * b: off + (i + 1) * b * b].view(b, b)
+        if not overwrite:
+            got = got - init[off + i * b * b: off + (i + 1) * b * b].view(b, b)
+        assert (got - ref).abs().max().item() <= 2e-5 * scale
